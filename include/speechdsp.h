@@ -1,0 +1,150 @@
+/* speechdsp.h — C ABI of the B200-native audio-DSP hot path of socom20/speech-cloner.
+ *
+ * The reference has no FFI: its boundary is `from audio_lib import ...`.
+ * Each entry point below is what a binding for that path would call; the reference
+ * interface it replaces is cited as /root/reference file:line.  All pointers named *_dev
+ * are CUDA device pointers owned by the caller, *_host are host pointers; `stream` is a
+ * cudaStream_t passed as void*.  Every call is stream-ordered and returns 0 on success or a
+ * negative sc_status; sc_last_error() gives the message.  No exceptions cross the ABI and
+ * there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Ragged batches: utterance u owns samples [sample_offsets[u], sample_offsets[u+1]) of the
+ * packed waveform buffer and frames [frame_offsets[u], frame_offsets[u+1]) of the packed,
+ * TIME-MAJOR feature buffers (row = frame, as audio_lib.py:207-211 returns them).  Gaps
+ * between utterances are allowed (offsets[u+1]-offsets[u] may exceed the utterance) when the
+ * explicit length arrays are given; see each call.
+ */
+#ifndef SPEECHDSP_H_
+#define SPEECHDSP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sc_plan sc_plan;
+
+typedef enum sc_status {
+    SC_OK = 0,
+    SC_ERR_INVALID = -1,     /* bad argument (ValueError on the Python side)           */
+    SC_ERR_CUDA = -2,        /* CUDA runtime error, message has cudaGetErrorString     */
+    SC_ERR_UNSUPPORTED = -3, /* parameter combination has no kernel                    */
+    SC_ERR_NO_DEVICE = -4    /* no CUDA device: the library never computes on the CPU  */
+} sc_status;
+
+/* DSP parameters = the hp/*.json keys that change front-end results (the md5 key list of
+ * TIMIT_reader.py:92-111) + calc_MFCC_input's keyword arguments (audio_lib.py:89-104). */
+typedef struct sc_params {
+    int32_t sample_rate;            /* sr                                   audio_lib.py:90  */
+    int32_t n_fft;                  /* n_fft (None -> win_length upstream)  audio_lib.py:135 */
+    int32_t win_length;             /* win_length                           audio_lib.py:93  */
+    int32_t hop_length;             /* hop_length                           audio_lib.py:92  */
+    int32_t n_mels;                 /* n_mels                               audio_lib.py:94  */
+    int32_t n_mfcc;                 /* n_mfcc                               audio_lib.py:95  */
+    int32_t mfcc_normalize_first;   /* mfcc_normaleze_first_mfcc            audio_lib.py:220 */
+    int32_t calc_mfcc_derivative;   /* calc_mfcc_derivate                   audio_lib.py:226 */
+    int32_t clip_output;            /* clip_output                          audio_lib.py:237 */
+    int32_t reserved0;
+    double pre_emphasis;            /* 0.0 disables the filter              audio_lib.py:129 */
+    double mfcc_norm_factor;        /*                                      audio_lib.py:223 */
+    double m_db_norm_factor;        /* 1.0 disables min-shift + scale       audio_lib.py:234 */
+    double p_db_norm_factor;        /* 1.0 disables min-shift + scale       audio_lib.py:230 */
+    double mean_abs_amp_norm;       /* 1.0 disables the gain                audio_lib.py:125 */
+    const double* window_host;      /* win_length periodic window samples
+                                       (scipy.signal.get_window(name, win, fftbins=True),
+                                       audio_lib.py:145); NULL -> Hann                        */
+} sc_params;
+
+/* Build the constant tables (window, W400 twiddles, sparse Slaney mel filterbank, DCT-II
+ * basis, window-sum-square) for one parameter set and upload them.  Replaces the per-call
+ * librosa.filters.mel / librosa.filters.dct rebuilds of audio_lib.py:160-166, :176. */
+int sc_plan_create(const sc_params* params, sc_plan** plan_out);
+void sc_plan_destroy(sc_plan* plan);
+
+/* 1 if (n_fft, hop_length) take the hand-tuned FFT-400 kernels, 0 for the generic-size kernels. */
+int sc_plan_is_fast_path(const sc_plan* plan);
+
+/* Number of frames librosa.stft(center=True) yields for n_samples: 1 + n_samples / hop. */
+int64_t sc_num_frames(const sc_plan* plan, int64_t n_samples);
+
+/* calc_MFCC_input over a ragged batch (audio_lib.py:89-244; callers TIMIT_reader.py:175,
+ * ARCTIC_reader.py:140, TARGET_spk_reader.py:156, test.py:474).
+ *   wav_dev          packed float32 waveforms
+ *   sample_offsets   n_utts+1 host int64; utterance u has sample_offsets[u+1]-sample_offsets[u]
+ *                    samples unless sample_lengths_host != NULL (then that many, rest is padding)
+ *   mfcc_dev         [frames][n_mfcc * (1 + calc_mfcc_derivative)] float32
+ *   mel_dev          [frames][n_mels] float32
+ *   pdb_dev          [frames][1 + n_fft/2] float32
+ *   frame_offsets    n_utts+1 host int64 row offsets; rows per utterance = sc_num_frames()
+ */
+int sc_frontend_batch(sc_plan* plan, const float* wav_dev, const int64_t* sample_offsets_host,
+                      const int64_t* sample_lengths_host, int32_t n_utts, float* mfcc_dev, float* mel_dev,
+                      float* pdb_dev, const int64_t* frame_offsets_host, void* stream);
+
+/* calc_preemphasis / calc_inv_preemphasis (audio_lib.py:12-28, :31-47): float32 in, float64 out
+ * (scipy.signal.lfilter promotes), zero initial state, one signal of n samples. */
+int sc_preemphasis(const float* wav_dev, int64_t n, double coeff, double* out_dev, void* stream);
+int sc_inv_preemphasis(const float* wav_dev, int64_t n, double coeff, double* out_dev, void* stream);
+
+/* Prologue of from_power_to_wav (audio_lib.py:290-298): P = max(0, P); optional `realse`
+ * power law with mean preservation; A = sqrt(10^(0.1 * (P / p_db_norm_factor - 80))).
+ * p_dev and amp_dev are time-major [frames][1 + n_fft/2]; may alias. */
+int sc_power_to_amp_batch(sc_plan* plan, const float* p_dev, const int64_t* frame_offsets_host,
+                          const int64_t* frame_counts_host, int32_t n_utts, double p_db_norm_factor,
+                          double realse, float* amp_dev, void* stream);
+
+/* griffin_lim_alg (audio_lib.py:249-274; only caller from_power_to_wav :299) over a ragged
+ * batch, from an injected initial phase (the reference draws np.pi*np.random.rand on the host,
+ * :255).  amp_dev / phase0_dev: time-major [frames][1 + n_fft/2] float32.  n_iters inverse
+ * STFTs and n_iters-1 forward STFTs are run, exactly like the reference loop.
+ *   wav_dev          packed float32 output, utterance u gets hop*(T_u-1) samples at sample_offsets[u]
+ *   rms_delta_dev    NULL, or [n_utts][n_iters] float32 receiving sqrt(mean((last-wav)^2)) per
+ *                    iteration (column 0 unused) — the value the reference prints when verbose (:262-264)
+ */
+int sc_griffinlim_batch(sc_plan* plan, const float* amp_dev, const float* phase0_dev,
+                        const int64_t* frame_offsets_host, const int64_t* frame_counts_host, int32_t n_utts,
+                        int32_t n_iters, float* wav_dev, const int64_t* sample_offsets_host,
+                        float* rms_delta_dev, void* stream);
+
+/* Epilogue of from_power_to_wav (audio_lib.py:301-306): optional de-emphasis IIR
+ * y[n] = x[n] + c*y[n-1] in float64, then y * (mean_abs_amp_norm / mean|y|).  coeff == 0 skips
+ * the filter.  wav_dev float32 in, out_dev float64 out, same ragged layout. */
+int sc_deemph_renorm_batch(sc_plan* plan, const float* wav_dev, const int64_t* sample_offsets_host,
+                           const int64_t* sample_lengths_host, int32_t n_utts, double coeff,
+                           double mean_abs_amp_norm, double* out_dev, void* stream);
+
+/* Layout helper for the reference's frequency-major arrays (librosa order, audio_lib.py:298
+ * transposes P.T): src [rows][cols] -> dst [cols][rows]; src_is_f64 selects float64 input.
+ * dst is always float32. */
+int sc_transpose_to_f32(const void* src_dev, int32_t src_is_f64, int64_t rows, int64_t cols, float* dst_dev,
+                        void* stream);
+
+/* One Griffin-Lim projection step on time-chunked long-form audio:
+ * same as one iteration of sc_griffinlim_batch for a single utterance, but the caller owns the
+ * waveform state, so ranks can exchange halos between calls.
+ *   first_frame / n_frames_total  position of this chunk inside the whole spectrogram
+ *   amp_dev          [n_frames_local][bins] magnitudes of frames first_frame ..
+ *   phase0_dev       NULL for a normal iteration; same shape as amp_dev for the initial inverse STFT
+ *   wav_in_dev       whole-signal coordinates are implied: element i is sample wav_first + i
+ *   wav_out_dev      receives samples [out_first, out_first + out_count)
+ */
+int sc_griffinlim_chunk_step(sc_plan* plan, const float* amp_dev, const float* phase0_dev, int64_t first_frame,
+                             int64_t n_frames_local, int64_t n_frames_total, const float* wav_in_dev,
+                             int64_t wav_first, int64_t wav_count, float* wav_out_dev, int64_t out_first,
+                             int64_t out_count, void* stream);
+
+/* Kernel launches issued by this library since the last reset (bench.py's gpu_launches). */
+int64_t sc_launch_count(void);
+void sc_launch_count_reset(void);
+
+/* Message of the last failing call on this thread ("" if none). */
+const char* sc_last_error(void);
+
+/* Library version string. */
+const char* sc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPEECHDSP_H_ */

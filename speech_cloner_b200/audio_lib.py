@@ -1,0 +1,504 @@
+"""Drop-in for the reference's ``audio_lib`` hot path, computed on a B200 by ``libspeechdsp.so``.
+
+``from speech_cloner_b200.audio_lib import calc_MFCC_input, from_power_to_wav, ...`` replaces
+``from audio_lib import ...`` (reference callers: TIMIT_reader.py:10, ARCTIC_reader.py:11,
+TARGET_spk_reader.py:11, test.py:23).  Signatures, argument order, defaults and the reference's
+spellings (``mfcc_normaleze_first_mfcc``, ``calc_mfcc_derivate``, ``realse``) are kept
+(/root/reference/audio_lib.py:12, :31, :51, :89-104, :249, :278-287).
+
+NumPy in -> freshly allocated NumPy out, like the reference.  Additionally every function accepts
+CUDA ``torch.Tensor`` inputs and then returns CUDA tensors without touching the host.  PyTorch is
+used only for device buffers and streams.  There is no CPU fallback: without the built library or
+without a GPU the calls raise.
+
+Extra keyword: ``phase0`` on ``griffin_lim_alg`` / ``from_power_to_wav`` injects the
+initial phase; ``None`` draws ``np.pi * np.random.rand(*stft_amp.shape)`` on the host from the
+global NumPy state exactly as audio_lib.py:255 does.
+
+Batched entry points (``calc_MFCC_input_batch``, ``from_power_to_wav_batch``) run the readers'
+``for i_sample in range(n_samples)`` loops (TIMIT_reader.py:169, ARCTIC_reader.py:134) as one
+ragged GPU batch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Optional, Sequence
+
+import numpy as np
+from scipy import signal as _signal
+
+from . import _lib
+
+__all__ = [
+    "calc_preemphasis", "calc_inv_preemphasis", "calc_PHN_target", "calc_MFCC_input",
+    "griffin_lim_alg", "from_power_to_wav", "calc_MFCC_input_batch", "from_power_to_wav_batch",
+    "griffin_lim_batch", "DspPlan", "FrontendLayout", "launch_count", "launch_count_reset",
+]
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _require_cuda():
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise _lib.SpeechDspError("no CUDA device available: speech_cloner_b200 has no CPU fallback")
+    return torch
+
+
+def _stream_ptr(torch) -> int:
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+# ----------------------------------------------------------------------------------- plans
+class DspPlan:
+    """Device-resident constant tables for one DSP parameter set (wraps ``sc_plan``)."""
+
+    _cache: dict = {}
+    _lock = threading.Lock()
+
+    def __init__(self, sr=16000, n_fft=400, win_length=400, hop_length=80, n_mels=80, n_mfcc=40,
+                 window="hann", pre_emphasis=0.97, mfcc_normaleze_first_mfcc=True, mfcc_norm_factor=0.01,
+                 calc_mfcc_derivate=False, M_dB_norm_factor=0.01, P_dB_norm_factor=0.01,
+                 mean_abs_amp_norm=0.003, clip_output=True):
+        lib = _lib.load()
+        _require_cuda()
+        if n_fft is None:
+            n_fft = win_length
+        win = _window_array(window, int(win_length))
+        prm = _lib.ScParams()
+        prm.sample_rate = int(sr); prm.n_fft = int(n_fft); prm.win_length = int(win_length)
+        prm.hop_length = int(hop_length); prm.n_mels = int(n_mels); prm.n_mfcc = int(n_mfcc)
+        prm.mfcc_normalize_first = int(bool(mfcc_normaleze_first_mfcc))
+        prm.calc_mfcc_derivative = int(bool(calc_mfcc_derivate))
+        prm.clip_output = int(bool(clip_output))
+        prm.pre_emphasis = float(pre_emphasis); prm.mfcc_norm_factor = float(mfcc_norm_factor)
+        prm.m_db_norm_factor = float(M_dB_norm_factor); prm.p_db_norm_factor = float(P_dB_norm_factor)
+        prm.mean_abs_amp_norm = float(mean_abs_amp_norm)
+        self._win = np.ascontiguousarray(win, dtype=np.float64)
+        prm.window_host = self._win.ctypes.data_as(C.POINTER(C.c_double))
+        handle = C.c_void_p()
+        _lib.check(lib.sc_plan_create(C.byref(prm), C.byref(handle)), "sc_plan_create")
+        self._h = handle
+        self._lib = lib
+        self.sr, self.n_fft, self.win_length, self.hop_length = int(sr), int(n_fft), int(win_length), int(hop_length)
+        self.n_mels, self.n_mfcc = int(n_mels), int(n_mfcc)
+        self.n_bins = 1 + self.n_fft // 2
+        self.mfcc_width = self.n_mfcc * (2 if calc_mfcc_derivate else 1)
+        self.fast_path = bool(lib.sc_plan_is_fast_path(handle))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._lib.sc_plan_destroy(h)
+            except Exception:
+                pass
+
+    @classmethod
+    def get(cls, **kw) -> "DspPlan":
+        """Cached plan (the reference rebuilds the mel / DCT matrices on every call, :160-176)."""
+        win = kw.get("window", "hann")
+        wkey = win if isinstance(win, (str, tuple, float, int)) else ("arr", np.asarray(win).tobytes())
+        torch = _require_cuda()
+        key = (torch.cuda.current_device(), wkey) + tuple(sorted((k, v) for k, v in kw.items() if k != "window"))
+        with cls._lock:
+            plan = cls._cache.get(key)
+            if plan is None:
+                plan = cls._cache[key] = cls(**kw)
+        return plan
+
+    def num_frames(self, n_samples: int) -> int:
+        return 1 + int(n_samples) // self.hop_length
+
+
+def _window_array(window, win_length: int) -> np.ndarray:
+    """librosa 0.6 ``filters.get_window(window, win_length, fftbins=True)`` (audio_lib.py:145)."""
+    if callable(window):
+        w = np.asarray(window(win_length), dtype=np.float64)
+    elif isinstance(window, (str, tuple)) or np.isscalar(window):
+        w = _signal.get_window(window, win_length, fftbins=True)
+    else:
+        w = np.asarray(window, dtype=np.float64)
+    if w.shape != (win_length,):
+        raise ValueError("window must have win_length samples")
+    return w
+
+
+# ------------------------------------------------------------------------- input validation
+def _valid_audio(y):
+    """librosa ``util.valid_audio`` as reached through ``stft``."""
+    if not isinstance(y, np.ndarray):
+        raise ValueError("data must be of type numpy.ndarray")
+    if not np.issubdtype(y.dtype, np.floating):
+        raise ValueError("data must be floating-point")
+    if y.ndim != 1:
+        raise ValueError("Invalid shape for monophonic audio: ndim={:d}, shape={}".format(y.ndim, y.shape))
+    if y.shape[0] == 0:
+        raise ValueError("audio buffer is empty")
+    if not np.isfinite(y).all():
+        raise ValueError("Audio buffer is not finite everywhere")
+
+
+def _is_tensor(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _to_dev_f32(x, torch):
+    """1-D/2-D float array or tensor -> contiguous float32 CUDA tensor."""
+    if _is_tensor(x):
+        return x.to(device="cuda", dtype=torch.float32).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).cuda()
+
+
+def _align(n: int, a: int) -> int:
+    return (n + a - 1) // a * a
+
+
+# ---------------------------------------------------------------------------- front-end
+class FrontendLayout:
+    """Packed ragged layout of a batch: 16-byte aligned utterance starts in every buffer."""
+
+    def __init__(self, lengths: Sequence[int], hop_length: int):
+        self.lengths = [int(n) for n in lengths]
+        self.frames = [1 + n // hop_length for n in self.lengths]
+        so, fo = [0], [0]
+        for n, t in zip(self.lengths, self.frames):
+            so.append(so[-1] + _align(n, 4))
+            fo.append(fo[-1] + _align(t, 4))
+        self.sample_offsets, self.frame_offsets = so, fo
+        self.total_samples, self.total_frames = so[-1], fo[-1]
+        self.c_sample_offsets = _lib.i64_array(so)
+        self.c_sample_lengths = _lib.i64_array(self.lengths)
+        self.c_frame_offsets = _lib.i64_array(fo)
+        self.c_frame_counts = _lib.i64_array(self.frames)
+
+
+def frontend_device(plan: DspPlan, wav_dev, layout: FrontendLayout, out=None):
+    """Run ``sc_frontend_batch`` on device buffers; returns (mfcc, mel, pdb) packed CUDA tensors."""
+    torch = _require_cuda()
+    if out is None:
+        out = (torch.empty((layout.total_frames, plan.mfcc_width), dtype=torch.float32, device="cuda"),
+               torch.empty((layout.total_frames, plan.n_mels), dtype=torch.float32, device="cuda"),
+               torch.empty((layout.total_frames, plan.n_bins), dtype=torch.float32, device="cuda"))
+    mfcc, mel, pdb = out
+    rc = plan._lib.sc_frontend_batch(plan._h, wav_dev.data_ptr(), layout.c_sample_offsets, layout.c_sample_lengths,
+                                     len(layout.lengths), mfcc.data_ptr(), mel.data_ptr(), pdb.data_ptr(),
+                                     layout.c_frame_offsets, _stream_ptr(torch))
+    _lib.check(rc, "sc_frontend_batch")
+    return out
+
+
+def _plan_from_kwargs(sr, pre_emphasis, hop_length, win_length, n_mels, n_mfcc, n_fft, window,
+                      mfcc_normaleze_first_mfcc, mfcc_norm_factor, calc_mfcc_derivate, M_dB_norm_factor,
+                      P_dB_norm_factor, mean_abs_amp_norm, clip_output) -> DspPlan:
+    if n_fft is None:
+        n_fft = win_length
+    return DspPlan.get(sr=sr, n_fft=int(n_fft), win_length=int(win_length), hop_length=int(hop_length),
+                       n_mels=int(n_mels), n_mfcc=int(n_mfcc), window=window, pre_emphasis=float(pre_emphasis),
+                       mfcc_normaleze_first_mfcc=bool(mfcc_normaleze_first_mfcc),
+                       mfcc_norm_factor=float(mfcc_norm_factor), calc_mfcc_derivate=bool(calc_mfcc_derivate),
+                       M_dB_norm_factor=float(M_dB_norm_factor), P_dB_norm_factor=float(P_dB_norm_factor),
+                       mean_abs_amp_norm=float(mean_abs_amp_norm), clip_output=bool(clip_output))
+
+
+def calc_MFCC_input_batch(wavs, sr=16000, pre_emphasis=0.97, hop_length=40, win_length=400, n_mels=128,
+                          n_mfcc=40, n_fft=None, window='hann', mfcc_normaleze_first_mfcc=True,
+                          mfcc_norm_factor=0.01, calc_mfcc_derivate=False, M_dB_norm_factor=0.01,
+                          P_dB_norm_factor=0.01, mean_abs_amp_norm=0.003, clip_output=True, return_device=False):
+    """``calc_MFCC_input`` over a list of waveforms as ONE ragged GPU batch.
+
+    Returns a list of ``(MFCC, M_dB, P_dB)`` triples (NumPy views of three packed host arrays, or
+    CUDA tensor views when ``return_device``), one per utterance, identical to calling the
+    reference function in a loop (TIMIT_reader.py:169-190).
+    """
+    wavs = list(wavs)
+    if not wavs:
+        return []
+    device_in = all(_is_tensor(w) for w in wavs)
+    if not device_in:
+        for w in wavs:
+            _valid_audio(w)                                   # before any device work, like librosa.stft
+    torch = _require_cuda()
+    plan = _plan_from_kwargs(sr, pre_emphasis, hop_length, win_length, n_mels, n_mfcc, n_fft, window,
+                             mfcc_normaleze_first_mfcc, mfcc_norm_factor, calc_mfcc_derivate, M_dB_norm_factor,
+                             P_dB_norm_factor, mean_abs_amp_norm, clip_output)
+    layout = FrontendLayout([int(w.shape[0]) for w in wavs], plan.hop_length)
+    if device_in:
+        wav_dev = torch.zeros(layout.total_samples, dtype=torch.float32, device="cuda")
+        for w, o in zip(wavs, layout.sample_offsets):
+            wav_dev[o:o + w.shape[0]] = w
+    else:
+        host = torch.zeros(layout.total_samples, dtype=torch.float32).pin_memory()
+        hv = host.numpy()
+        for w, o in zip(wavs, layout.sample_offsets):
+            hv[o:o + w.shape[0]] = w
+        wav_dev = host.to("cuda", non_blocking=True)
+    mfcc, mel, pdb = frontend_device(plan, wav_dev, layout)
+    if not (return_device or device_in):
+        mfcc, mel, pdb = mfcc.cpu().numpy(), mel.cpu().numpy(), pdb.cpu().numpy()
+    out = []
+    for o, t in zip(layout.frame_offsets, layout.frames):
+        out.append((mfcc[o:o + t], mel[o:o + t], pdb[o:o + t]))
+    return out
+
+
+def calc_MFCC_input(y,
+                    sr=16000,
+                    pre_emphasis=0.97,
+                    hop_length=40,
+                    win_length=400,
+                    n_mels=128,
+                    n_mfcc=40,
+                    n_fft=None,
+                    window='hann',
+                    mfcc_normaleze_first_mfcc=True,
+                    mfcc_norm_factor=0.01,
+                    calc_mfcc_derivate=False,
+                    M_dB_norm_factor=0.01,
+                    P_dB_norm_factor=0.01,
+                    mean_abs_amp_norm=0.003,
+                    clip_output=True):
+    """Waveform -> (MFCC (T, n_mfcc[*2]), M_dB (T, n_mels), P_dB (T, 1+n_fft//2)), float32, time-major.
+
+    Same contract as /root/reference/audio_lib.py:89-244.
+    """
+    res = calc_MFCC_input_batch([y], sr=sr, pre_emphasis=pre_emphasis, hop_length=hop_length,
+                                win_length=win_length, n_mels=n_mels, n_mfcc=n_mfcc, n_fft=n_fft, window=window,
+                                mfcc_normaleze_first_mfcc=mfcc_normaleze_first_mfcc,
+                                mfcc_norm_factor=mfcc_norm_factor, calc_mfcc_derivate=calc_mfcc_derivate,
+                                M_dB_norm_factor=M_dB_norm_factor, P_dB_norm_factor=P_dB_norm_factor,
+                                mean_abs_amp_norm=mean_abs_amp_norm, clip_output=clip_output)[0]
+    if _is_tensor(res[0]):
+        return tuple(r.clone() for r in res)
+    return tuple(np.ascontiguousarray(r) for r in res)
+
+
+# -------------------------------------------------------------------- pre- / de-emphasis
+def _emphasis(wav, coeff, inverse: bool):
+    torch = _require_cuda()
+    lib = _lib.load()
+    device_in = _is_tensor(wav)
+    if not device_in:
+        wav = np.asarray(wav)
+        if wav.ndim != 1:
+            raise ValueError("wav must be one-dimensional")
+    x = _to_dev_f32(wav, torch)
+    out = torch.empty(x.shape[0], dtype=torch.float64, device="cuda")
+    fn = lib.sc_inv_preemphasis if inverse else lib.sc_preemphasis
+    _lib.check(fn(x.data_ptr(), x.shape[0], float(coeff), out.data_ptr(), _stream_ptr(torch)),
+               "sc_inv_preemphasis" if inverse else "sc_preemphasis")
+    return out if device_in else out.cpu().numpy()
+
+
+def calc_preemphasis(wav, coeff=0.97):
+    """y[n] = x[n] - coeff * x[n-1], zero initial state, float64 (audio_lib.py:12-28)."""
+    return _emphasis(wav, coeff, inverse=False)
+
+
+def calc_inv_preemphasis(preem_wav, coeff=0.97):
+    """y[n] = x[n] + coeff * y[n-1], zero initial state, float64 (audio_lib.py:31-47)."""
+    return _emphasis(preem_wav, coeff, inverse=True)
+
+
+def calc_PHN_target(y, phn_v, phn_conv_d, hop_length=40, win_length=400):
+    """Per-frame phoneme label by larger window overlap (audio_lib.py:51-85); host integer logic.
+
+    Out of the GPU hot path (SURVEY.md §2.1 #5, §8(f) "next"); kept so that the readers' loop
+    (TIMIT_reader.py:192) finds the whole ``audio_lib`` surface here.
+    """
+    n_frames = int(y.shape[0] / hop_length) + 1
+    starts = np.asarray([p[0] for p in phn_v], dtype=np.int64)
+    ends = np.asarray([p[1] for p in phn_v], dtype=np.int64)
+    last = len(phn_v) - 1
+    lo = np.arange(n_frames, dtype=np.int64) * hop_length - win_length // 2
+    hi = lo + win_length
+    # the reference cursor only moves forward while ends[cur] <= lo: that is a running maximum of
+    # "first interval whose end exceeds lo" over frames (lo is increasing)
+    cur = np.empty(n_frames, dtype=np.int64)
+    c = 0
+    for t in range(n_frames):
+        while ends[c] <= lo[t] and c < last:
+            c += 1
+        cur[t] = c
+    nxt = np.minimum(cur + 1, last)
+    ov_cur = np.minimum(ends[cur], hi) - np.maximum(starts[cur], lo)
+    ov_nxt = np.minimum(ends[nxt], hi) - np.maximum(starts[nxt], lo)
+    pick = np.where((cur < last) & (ov_cur < ov_nxt), nxt, cur)
+    return np.array([phn_conv_d[phn_v[i][2]] for i in pick], dtype=np.int32)
+
+
+# --------------------------------------------------------------------------- Griffin-Lim
+def _gl_plan(win_length, hop_length, n_fft) -> DspPlan:
+    if n_fft is None:
+        n_fft = win_length
+    return DspPlan.get(n_fft=int(n_fft), win_length=int(win_length), hop_length=int(hop_length))
+
+
+def _freq_major_to_dev(x, n_bins: int, torch, lib):
+    """(n_bins, T) float32/float64 array or tensor -> [T][n_bins] float32 CUDA tensor."""
+    if _is_tensor(x):
+        src = x.to(device="cuda").contiguous()
+        if src.dtype not in (torch.float32, torch.float64):
+            src = src.to(torch.float32)
+    else:
+        a = np.ascontiguousarray(x)
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float32)
+        src = torch.from_numpy(a).cuda()
+    if src.ndim != 2 or src.shape[0] != n_bins:
+        raise ValueError("expected a (1 + n_fft//2, T) array, got {}".format(tuple(src.shape)))
+    T = src.shape[1]
+    dst = torch.empty((T, n_bins), dtype=torch.float32, device="cuda")
+    _lib.check(lib.sc_transpose_to_f32(src.data_ptr(), int(src.dtype == torch.float64), n_bins, T,
+                                       dst.data_ptr(), _stream_ptr(torch)), "sc_transpose_to_f32")
+    return dst
+
+
+class _GlLayout:
+    def __init__(self, frames: Sequence[int], hop: int):
+        self.frames = [int(t) for t in frames]
+        self.samples = [hop * (t - 1) for t in self.frames]
+        fo, so = [0], [0]
+        for t, n in zip(self.frames, self.samples):
+            fo.append(fo[-1] + _align(t, 4))
+            so.append(so[-1] + _align(max(n, 1), 4))
+        self.frame_offsets, self.sample_offsets = fo, so
+        self.c_frame_offsets = _lib.i64_array(fo)
+        self.c_frame_counts = _lib.i64_array(self.frames)
+        self.c_sample_offsets = _lib.i64_array(so)
+        self.c_sample_lengths = _lib.i64_array(self.samples)
+
+
+def griffin_lim_device(plan: DspPlan, amp_dev, phase0_dev, layout: "_GlLayout", n_iters: int, rms=None, wav_out=None):
+    """``sc_griffinlim_batch`` on packed time-major device buffers; returns the packed float32 waveforms."""
+    torch = _require_cuda()
+    if wav_out is None:
+        wav_out = torch.empty(layout.sample_offsets[-1], dtype=torch.float32, device="cuda")
+    rc = plan._lib.sc_griffinlim_batch(plan._h, amp_dev.data_ptr(), phase0_dev.data_ptr(), layout.c_frame_offsets,
+                                       layout.c_frame_counts, len(layout.frames), int(n_iters), wav_out.data_ptr(),
+                                       layout.c_sample_offsets, rms.data_ptr() if rms is not None else None,
+                                       _stream_ptr(torch))
+    _lib.check(rc, "sc_griffinlim_batch")
+    return wav_out
+
+
+def _print_rms(rms_row):
+    for i in range(1, len(rms_row)):
+        print(' i={}  mrse_delta = {}'.format(i, rms_row[i]))
+
+
+def griffin_lim_alg(stft_amp, win_length, hop_length, num_iters=300, n_fft=None, verbose=True, phase0=None):
+    """Griffin-Lim from a (1+n_fft//2, T) magnitude; returns float32 (hop*(T-1),) (audio_lib.py:249-274)."""
+    torch = _require_cuda()
+    lib = _lib.load()
+    plan = _gl_plan(win_length, hop_length, n_fft)
+    device_in = _is_tensor(stft_amp)
+    shape = tuple(stft_amp.shape)
+    if len(shape) != 2 or shape[0] != plan.n_bins:
+        raise ValueError("stft_amp must have shape (1 + n_fft//2, T)")
+    if shape[1] < 2:
+        raise ValueError("stft_amp needs at least 2 frames")
+    if phase0 is None:
+        phase0 = np.pi * np.random.rand(*shape)                       # :255, global NumPy state
+    amp = _freq_major_to_dev(stft_amp, plan.n_bins, torch, lib)
+    ph = _freq_major_to_dev(phase0, plan.n_bins, torch, lib)
+    layout = _GlLayout([shape[1]], plan.hop_length)
+    rms = torch.zeros((1, int(num_iters)), dtype=torch.float32, device="cuda") if verbose else None
+    wav = griffin_lim_device(plan, amp, ph, layout, int(num_iters), rms)[: layout.samples[0]]
+    if verbose:
+        _print_rms(rms[0].cpu().numpy())
+    return wav.clone() if device_in else wav.cpu().numpy()
+
+
+def griffin_lim_batch(amps, win_length, hop_length, num_iters=300, n_fft=None, phase0s=None, return_device=False):
+    """``griffin_lim_alg`` over a list of TIME-MAJOR (T, bins) magnitudes as one ragged GPU batch."""
+    torch = _require_cuda()
+    plan = _gl_plan(win_length, hop_length, n_fft)
+    amps = list(amps)
+    layout = _GlLayout([a.shape[0] for a in amps], plan.hop_length)
+    amp_dev = torch.zeros((layout.frame_offsets[-1], plan.n_bins), dtype=torch.float32, device="cuda")
+    ph_dev = torch.zeros_like(amp_dev)
+    for i, (a, o) in enumerate(zip(amps, layout.frame_offsets)):
+        amp_dev[o:o + a.shape[0]] = _to_dev_f32(a, torch)
+        p = phase0s[i] if phase0s is not None else np.pi * np.random.rand(plan.n_bins, a.shape[0]).T
+        ph_dev[o:o + a.shape[0]] = _to_dev_f32(p, torch)
+    wav = griffin_lim_device(plan, amp_dev, ph_dev, layout, int(num_iters))
+    outs = [wav[o:o + n] for o, n in zip(layout.sample_offsets, layout.samples)]
+    return outs if return_device else [w.cpu().numpy() for w in outs]
+
+
+def from_power_to_wav_batch(Ps, P_dB_norm_factor=0.01, pre_emphasis=0.97, hop_length=40, win_length=800,
+                            mean_abs_amp_norm=0.01, n_iter=200, n_fft=None, realse=1.0, verbose=False,
+                            phase0s=None, return_device=False):
+    """``from_power_to_wav`` over a list of (T, bins) spectrograms as one ragged GPU batch.
+
+    ``phase0s`` is a list of (bins, T) initial phases (reference orientation) or ``None``.
+    """
+    torch = _require_cuda()
+    lib = _lib.load()
+    plan = _gl_plan(win_length, hop_length, n_fft)
+    Ps = list(Ps)
+    for P in Ps:
+        if len(P.shape) != 2 or P.shape[1] != plan.n_bins:
+            raise ValueError("P must have shape (T, 1 + n_fft//2)")
+        if P.shape[0] < 2:
+            raise ValueError("P needs at least 2 frames")
+    layout = _GlLayout([P.shape[0] for P in Ps], plan.hop_length)
+    n = len(Ps)
+    p_dev = torch.zeros((layout.frame_offsets[-1], plan.n_bins), dtype=torch.float32, device="cuda")
+    ph_dev = torch.zeros_like(p_dev)
+    for i, (P, o) in enumerate(zip(Ps, layout.frame_offsets)):
+        p_dev[o:o + P.shape[0]] = _to_dev_f32(P, torch)
+        ph = phase0s[i] if phase0s is not None else np.pi * np.random.rand(plan.n_bins, P.shape[0])
+        ph_dev[o:o + P.shape[0]] = _freq_major_to_dev(ph, plan.n_bins, torch, lib)
+    st = _stream_ptr(torch)
+    amp_dev = torch.empty_like(p_dev)
+    _lib.check(lib.sc_power_to_amp_batch(plan._h, p_dev.data_ptr(), layout.c_frame_offsets, layout.c_frame_counts,
+                                         n, float(P_dB_norm_factor), float(realse), amp_dev.data_ptr(), st),
+               "sc_power_to_amp_batch")
+    rms = torch.zeros((n, int(n_iter)), dtype=torch.float32, device="cuda") if verbose else None
+    wav = griffin_lim_device(plan, amp_dev, ph_dev, layout, int(n_iter), rms)
+    if verbose:
+        _print_rms(rms[0].cpu().numpy())
+    out = torch.empty(layout.sample_offsets[-1], dtype=torch.float64, device="cuda")
+    _lib.check(lib.sc_deemph_renorm_batch(plan._h, wav.data_ptr(), layout.c_sample_offsets, layout.c_sample_lengths,
+                                          n, float(pre_emphasis), float(mean_abs_amp_norm), out.data_ptr(), st),
+               "sc_deemph_renorm_batch")
+    outs = [out[o:o + m] for o, m in zip(layout.sample_offsets, layout.samples)]
+    return outs if return_device else [w.cpu().numpy() for w in outs]
+
+
+def from_power_to_wav(P,
+                      P_dB_norm_factor=0.01,
+                      pre_emphasis=0.97,
+                      hop_length=40,
+                      win_length=800,
+                      mean_abs_amp_norm=0.01,
+                      n_iter=200,
+                      n_fft=None,
+                      realse=1.0,
+                      verbose=True,
+                      phase0=None):
+    """Normalised power-dB map (T, 1+n_fft//2) -> waveform float64 (hop*(T-1),) (audio_lib.py:278-308)."""
+    device_in = _is_tensor(P)
+    res = from_power_to_wav_batch([P], P_dB_norm_factor=P_dB_norm_factor, pre_emphasis=pre_emphasis,
+                                  hop_length=hop_length, win_length=win_length, mean_abs_amp_norm=mean_abs_amp_norm,
+                                  n_iter=n_iter, n_fft=n_fft, realse=realse, verbose=verbose,
+                                  phase0s=None if phase0 is None else [phase0], return_device=device_in)[0]
+    if device_in:
+        return res.clone()
+    # without de-emphasis the reference never leaves float32 (:304-306)
+    return res.astype(np.float32) if pre_emphasis == 0 else res
+
+
+def launch_count() -> int:
+    """Kernels launched by the library since the last reset (bench.py's ``gpu_launches``)."""
+    return int(_lib.load().sc_launch_count())
+
+
+def launch_count_reset() -> None:
+    _lib.load().sc_launch_count_reset()

@@ -1,0 +1,399 @@
+// Front-end kernels (fast path: n_fft = 400, hop = 80): calc_MFCC_input, audio_lib.py:89-244.
+//
+//   k_abs_partial / k_gain_finalize   mean|y| gain                               :125-126
+//   k_fe_pass_a   gain -> pre-emphasis -> reflect pad -> window -> rFFT-400 -> |X|^2
+//                 -> raw 10*log10 power, sparse Slaney mel -> raw mel dB, utterance max/min   :129-172
+//   k_fe_pass_b   top_db clip, min shift, scale, clip; DCT-II, c0 shift, delta, clip         :157, :172-244
+//
+// The utterance-wide max / min (librosa's top_db = 80 floor and the min shift) split the work in
+// two passes; pass A leaves raw dB values in the output buffers (L2 resident for batches that
+// fit), pass B normalises them in place.
+#pragma once
+#include "common.cuh"
+#include "fft400.cuh"
+
+namespace scdsp {
+
+struct FeTables {
+    const float2* w400;        // W400^m = exp(-2*pi*i*m/400), m in [0, 400)
+    const float* win_half;     // 0.5 * analysis window, centre padded to 400
+    const float2* mel_w;       // per bin: (weight into band i(k), weight into band i(k)-1)
+    const int32_t* mel_istart; // first bin of mel interval i, i in [0, n_mels + 1]; [n_mels+1] = bins
+    const int32_t* mel_chunk;  // band boundaries of the kMaxMelChunks work chunks
+    const float* dct_t;        // DCT-II basis transposed: dct_t[m * n_mfcc_pad + q]
+    int32_t n_mels;
+    int32_t n_mfcc;
+    int32_t n_mfcc_pad;        // n_mfcc rounded up to a multiple of 8
+};
+
+struct FeParams {
+    double pre_emphasis;
+    double mean_abs_amp_norm;
+    float mfcc_norm_factor;
+    float m_db_norm_factor;
+    float p_db_norm_factor;
+    int32_t use_gain, norm_first, use_delta, clip, shift_p, shift_m;
+};
+
+// ---------------------------------------------------------------------------------------------
+// mean|y| : per-(utterance, chunk) float64 partial sums, then one warp per utterance adds them in
+// a fixed order (deterministic) and writes the gain.
+constexpr int kAbsChunk = 8192;
+
+__global__ void __launch_bounds__(256) k_abs_partial(const float* __restrict__ wav, Ragged rg,
+                                                     double* __restrict__ partial) {
+    const int tile = blockIdx.x;
+    const int u = find_utt(rg.tile_prefix, rg.n_utts, tile);
+    const int64_t begin = (int64_t)(tile - rg.tile_prefix[u]) * kAbsChunk;
+    const int64_t len = rg.sample_len[u];
+    const int64_t end = begin + kAbsChunk < len ? begin + kAbsChunk : len;
+    const float* __restrict__ y = wav + rg.sample_off[u];
+    double s = 0.0;
+    for (int64_t i = begin + threadIdx.x; i < end; i += 256) s += (double)fabsf(__ldg(y + i));
+    s = warp_sum(s);
+    __shared__ double red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w];
+        partial[tile] = t;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_gain_finalize(Ragged rg, const double* __restrict__ partial,
+                                                       UttStat* __restrict__ stat, double mean_abs_amp_norm,
+                                                       int use_gain) {
+    const int u = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (u >= rg.n_utts) return;
+    const int lane = threadIdx.x & 31;
+    float gain = 1.0f;
+    if (use_gain) {
+        double s = 0.0;
+        for (int t = rg.tile_prefix[u] + lane; t < rg.tile_prefix[u + 1]; t += 32) s += partial[t];
+        s = warp_sum(s);
+        // np.abs(y).mean() is a float32; python float / float32 was a float64 in the reference era
+        const float mean32 = (float)(s / (double)rg.sample_len[u]);
+        gain = (float)(mean_abs_amp_norm / (double)mean32);
+    }
+    if (lane == 0) {
+        UttStat st;
+        st.gain = gain;
+        st.p_max = 0u; st.m_max = 0u;
+        st.p_min = 0x7f800000u; st.m_min = 0x7f800000u;
+        st.pad[0] = st.pad[1] = st.pad[2] = 0.f;
+        stat[u] = st;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shared tail of pass A (fast and generic-size kernels): `power` holds |X|^2 of F frames.
+//   raw power dB (:157 without the top_db clip)  -> pdb_dst  (coalesced)
+//   sparse Slaney mel (:160-169) + raw amplitude_to_db (:172) -> mel_dst
+//   utterance max / min of the power and of the mel power   -> stat (order-independent atomics)
+template <int THREADS>
+__device__ __forceinline__ void fe_epilogue_a(const float* __restrict__ power, int F, int bins, int nfr,
+                                              const float2* __restrict__ mel_w_s, const int32_t* __restrict__ istart_s,
+                                              const FeTables& tb, float* __restrict__ mel_db,
+                                              float (*red)[THREADS / 32], UttStat* __restrict__ stat_u,
+                                              float* __restrict__ pdb_dst, float* __restrict__ mel_dst) {
+    const int tid = threadIdx.x;
+    const int n_mels = tb.n_mels;
+    const int mel_ld = n_mels + 1;
+    float p_max = 0.f, p_min = __int_as_float(0x7f800000), m_max = 0.f, m_min = __int_as_float(0x7f800000);
+    {
+        const int n = nfr * bins;
+        for (int e = tid; e < n; e += THREADS) {
+            const float p = power[e];
+            p_max = fmaxf(p_max, p);
+            p_min = fminf(p_min, p);
+            pdb_dst[e] = db10(fmaxf(p, 1e-10f));
+        }
+    }
+    // thread = (frame, band chunk); every lane of a warp walks the same bins => uniform control flow
+    if (tid < F * kMaxMelChunks) {
+        const int f = tid % F;
+        const int q = tid / F;
+        const int mb = __ldg(tb.mel_chunk + q), me = __ldg(tb.mel_chunk + q + 1);
+        if (f < nfr && me > mb) {
+            const float* __restrict__ prow = power + f * bins;
+            float prev_up = 0.f;
+            for (int i = mb; i <= me; ++i) {
+                float a_up = 0.f, a_dn = 0.f;
+                const int k1 = istart_s[i + 1];
+                for (int k = istart_s[i]; k < k1; ++k) {
+                    const float p = prow[k];
+                    const float2 w = mel_w_s[k];
+                    a_up = fmaf(w.x, p, a_up);
+                    a_dn = fmaf(w.y, p, a_dn);
+                }
+                if (i > mb) {
+                    const float m = prev_up + a_dn;
+                    m_max = fmaxf(m_max, m);
+                    m_min = fminf(m_min, m);
+                    mel_db[f * mel_ld + (i - 1)] = 2.0f * db10(fmaxf(m, 1e-5f));
+                }
+                prev_up = a_up;
+            }
+        }
+    }
+    p_max = warp_max(p_max); p_min = warp_min(p_min);
+    m_max = warp_max(m_max); m_min = warp_min(m_min);
+    if ((tid & 31) == 0) {
+        red[0][tid >> 5] = p_max; red[1][tid >> 5] = p_min;
+        red[2][tid >> 5] = m_max; red[3][tid >> 5] = m_min;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < THREADS / 32; ++w) {
+            p_max = fmaxf(p_max, red[0][w]); p_min = fminf(p_min, red[1][w]);
+            m_max = fmaxf(m_max, red[2][w]); m_min = fminf(m_min, red[3][w]);
+        }
+        atomicMax(&stat_u->p_max, __float_as_uint(p_max));
+        atomicMin(&stat_u->p_min, __float_as_uint(p_min));
+        atomicMax(&stat_u->m_max, __float_as_uint(m_max));
+        atomicMin(&stat_u->m_min, __float_as_uint(m_min));
+    }
+    {
+        const int n = nfr * n_mels;
+        for (int e = tid; e < n; e += THREADS) {
+            const int f = e / n_mels;
+            mel_dst[e] = mel_db[f * mel_ld + (e - f * n_mels)];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass A.  One CTA = 32 consecutive frames of one utterance = 16 units x 20 threads.
+struct FeSmemA {
+    float span[kFeSpan];                       // pre-emphasised, reflect-padded samples of the tile
+    float win[kNfft];
+    float2 slots[kFeUnits * kUnitSlots];       // step-1 -> step-2 exchange
+    float power[kFeFrames * kBins];            // |X|^2, row = frame
+    float2 mel_w[kBins];
+    int32_t mel_istart[kMaxMels + 2];
+    float red[4][kFeThreads / 32];
+    // followed by mel_db[kFeFrames][n_mels + 1]
+};
+
+__global__ void __launch_bounds__(kFeThreads, 2)
+k_fe_pass_a(const float* __restrict__ wav, Ragged rg, FeTables tb, FeParams prm, UttStat* __restrict__ stat,
+            float* __restrict__ pdb_out, float* __restrict__ mel_raw) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FeSmemA& sm = *reinterpret_cast<FeSmemA*>(smem_raw);
+    float* mel_db = reinterpret_cast<float*>(smem_raw + sizeof(FeSmemA));
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int u = find_utt(rg.tile_prefix, rg.n_utts, tile);
+    const int t0 = (tile - rg.tile_prefix[u]) * kFeFrames;
+    const int T = rg.frame_cnt[u];
+    const int nfr = min(kFeFrames, T - t0);
+    const int64_t L = rg.sample_len[u];
+    const float* __restrict__ y = wav + rg.sample_off[u];
+    const float gain = stat[u].gain;
+    const int n_mels = tb.n_mels;
+
+    // ---- stage: gain (float32, :126) -> pre-emphasis in float64 (:27) -> reflect pad (:147)
+    {
+        const int64_t q0 = (int64_t)t0 * kHop - kNfft / 2;
+        const double c = prm.pre_emphasis;
+        for (int i = tid; i < kFeSpan; i += kFeThreads) {
+            const int64_t r = reflect_idx(q0 + i, L);
+            const float cur = gain * __ldg(y + r);
+            const float prev = r > 0 ? gain * __ldg(y + r - 1) : 0.0f;
+            sm.span[i] = (float)((double)cur - c * (double)prev);
+        }
+        for (int i = tid; i < kNfft; i += kFeThreads) sm.win[i] = tb.win_half[i];
+        for (int i = tid; i < kBins; i += kFeThreads) sm.mel_w[i] = tb.mel_w[i];
+        for (int i = tid; i < n_mels + 2; i += kFeThreads) sm.mel_istart[i] = tb.mel_istart[i];
+    }
+    const int unit = tid / kUnitThreads;
+    const int j = tid - unit * kUnitThreads;
+    Twiddle tw;
+    load_twiddles(tw, tb.w400, j);
+    __syncthreads();
+
+    // ---- step 1: frames A = 2*unit, B = A + 1 share 24 strided samples (hop = 4 * 20)
+    float2* unit_slots = sm.slots + unit * kUnitSlots;
+    {
+        float s[24];
+        const float* __restrict__ src = sm.span + unit * (2 * kHop) + j;
+#pragma unroll
+        for (int m = 0; m < 24; ++m) s[m] = src[20 * m];
+        float2 z[20];
+#pragma unroll
+        for (int n1 = 0; n1 < 20; ++n1) {
+            const float w = sm.win[20 * n1 + j];
+            z[n1] = make_float2(s[n1] * w, s[n1 + 4] * w);
+        }
+        fwd_step1(z, tw, unit_slots + j);
+    }
+    __syncthreads();
+    // ---- step 2 + |X|^2
+    {
+        float2 v[20];
+        fwd_step2(v, unit_slots + j * kSlotLd);
+        float* pa = sm.power + (2 * unit) * kBins;
+        store_power(v, j, pa, pa + kBins);
+    }
+    __syncthreads();
+
+    fe_epilogue_a<kFeThreads>(sm.power, kFeFrames, kBins, nfr, sm.mel_w, sm.mel_istart, tb, mel_db, sm.red,
+                              stat + u, pdb_out + (rg.frame_off[u] + t0) * kBins,
+                              mel_raw + (rg.frame_off[u] + t0) * n_mels);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass B.  One CTA = 128 consecutive frames of one utterance.
+constexpr int kFbFrames = 128;
+constexpr int kFbThreads = 256;
+
+__global__ void __launch_bounds__(kFbThreads)
+k_fe_pass_b(Ragged rg, FeTables tb, FeParams prm, const UttStat* __restrict__ stat,
+            const float* __restrict__ mel_raw, float* __restrict__ pdb, float* __restrict__ mel_out,
+            float* __restrict__ mfcc_out, int n_bins) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int u = find_utt(rg.tile_prefix, rg.n_utts, tile);
+    const int t0 = (tile - rg.tile_prefix[u]) * kFbFrames;
+    const int T = rg.frame_cnt[u];
+    const int nfr = min(kFbFrames, T - t0);
+    const UttStat st = stat[u];
+    const int n_mels = tb.n_mels, n_mfcc = tb.n_mfcc, n_pad = tb.n_mfcc_pad;
+    const int mel_ld = n_mels + 1, cc_ld = n_pad + 1;
+
+    float* dct_s = reinterpret_cast<float*>(smem_raw);               // [n_mels][n_pad]
+    float* mel_s = dct_s + n_mels * n_pad;                           // [kFbFrames + 2][mel_ld]
+    float* cc_s = mel_s + (kFbFrames + 2) * mel_ld;                  // [kFbFrames + 2][cc_ld]
+    float* c00_s = cc_s + (kFbFrames + 2) * cc_ld;                   // [1]
+
+    // ---- power dB: top_db clip (:157), min shift + scale (:231), clip (:239); in place
+    {
+        const float hi = db10(fmaxf(__uint_as_float(st.p_max), 1e-10f));
+        const float floor_db = hi - 80.0f;
+        const float lo = fmaxf(db10(fmaxf(__uint_as_float(st.p_min), 1e-10f)), floor_db);
+        const float sub = prm.shift_p ? lo : 0.0f;
+        const float mul = prm.shift_p ? prm.p_db_norm_factor : 1.0f;
+        const int64_t base = (rg.frame_off[u] + t0) * n_bins;
+        const int n = nfr * n_bins;
+        float* __restrict__ p = pdb + base;
+        if ((base & 3) == 0) {
+            float4* __restrict__ p4 = reinterpret_cast<float4*>(p);
+            const int n4 = n >> 2;
+            for (int e = tid; e < n4; e += kFbThreads) {
+                float4 v = p4[e];
+                v.x = mul * (fmaxf(v.x, floor_db) - sub); v.y = mul * (fmaxf(v.y, floor_db) - sub);
+                v.z = mul * (fmaxf(v.z, floor_db) - sub); v.w = mul * (fmaxf(v.w, floor_db) - sub);
+                if (prm.clip) {
+                    v.x = fminf(fmaxf(v.x, -1.f), 1.f); v.y = fminf(fmaxf(v.y, -1.f), 1.f);
+                    v.z = fminf(fmaxf(v.z, -1.f), 1.f); v.w = fminf(fmaxf(v.w, -1.f), 1.f);
+                }
+                p4[e] = v;
+            }
+            for (int e = (n4 << 2) + tid; e < n; e += kFbThreads) {
+                float v = mul * (fmaxf(p[e], floor_db) - sub);
+                if (prm.clip) v = fminf(fmaxf(v, -1.f), 1.f);
+                p[e] = v;
+            }
+        } else {
+            for (int e = tid; e < n; e += kFbThreads) {
+                float v = mul * (fmaxf(p[e], floor_db) - sub);
+                if (prm.clip) v = fminf(fmaxf(v, -1.f), 1.f);
+                p[e] = v;
+            }
+        }
+    }
+
+    // ---- mel dB rows t0-1 .. t0+nfr (halo for the delta), top_db clip (:172)
+    const float m_hi = 2.0f * db10(fmaxf(__uint_as_float(st.m_max), 1e-5f));
+    const float m_floor = m_hi - 80.0f;
+    const float m_lo = fmaxf(2.0f * db10(fmaxf(__uint_as_float(st.m_min), 1e-5f)), m_floor);
+    {
+        const float* __restrict__ src = mel_raw + rg.frame_off[u] * n_mels;
+        const int n = (nfr + 2) * n_mels;
+        for (int e = tid; e < n; e += kFbThreads) {
+            const int r = e / n_mels;
+            const int t = t0 - 1 + r;
+            const int m = e - r * n_mels;
+            float v = 0.f;
+            if (t >= 0 && t < T) v = fmaxf(__ldg(src + (int64_t)t * n_mels + m), m_floor);
+            mel_s[r * mel_ld + m] = v;
+        }
+        for (int e = tid; e < n_mels * n_pad; e += kFbThreads) dct_s[e] = tb.dct_t[e];
+        // MFCC[0, 0] of the utterance (:221): first DCT row applied to frame 0
+        if (tid < 32) {
+            float a = 0.f;
+            if (prm.norm_first)
+                for (int m = tid; m < n_mels; m += 32)
+                    a = fmaf(__ldg(tb.dct_t + m * n_pad), fmaxf(__ldg(src + m), m_floor), a);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (tid == 0) c00_s[0] = a;
+        }
+    }
+    __syncthreads();
+
+    // ---- normalised mel output (:235, :240)
+    {
+        const float sub = prm.shift_m ? m_lo : 0.0f;
+        const float mul = prm.shift_m ? prm.m_db_norm_factor : 1.0f;
+        float* __restrict__ dst = mel_out + (rg.frame_off[u] + t0) * n_mels;
+        const int n = nfr * n_mels;
+        for (int e = tid; e < n; e += kFbThreads) {
+            const int r = e / n_mels;
+            float v = mul * (mel_s[(r + 1) * mel_ld + (e - r * n_mels)] - sub);
+            if (prm.clip) v = fminf(fmaxf(v, -1.f), 1.f);
+            dst[e] = v;
+        }
+    }
+    // ---- DCT-II (:176-179), c0 shift (:221), scale (:224): task = (frame row, group of 8 coefficients)
+    {
+        const int groups = n_pad >> 3;
+        const int rows = nfr + 2;
+        const float c00 = c00_s[0];
+        for (int task = tid; task < rows * groups; task += kFbThreads) {
+            const int g = task / rows;
+            const int r = task - g * rows;
+            const float* __restrict__ x = mel_s + r * mel_ld;
+            const float4* __restrict__ d = reinterpret_cast<const float4*>(dct_s + 8 * g);
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int m = 0; m < n_mels; ++m) {
+                const float xv = x[m];
+                const float4 d0 = d[(m * n_pad) >> 2], d1 = d[((m * n_pad) >> 2) + 1];
+                acc[0] = fmaf(d0.x, xv, acc[0]); acc[1] = fmaf(d0.y, xv, acc[1]);
+                acc[2] = fmaf(d0.z, xv, acc[2]); acc[3] = fmaf(d0.w, xv, acc[3]);
+                acc[4] = fmaf(d1.x, xv, acc[4]); acc[5] = fmaf(d1.y, xv, acc[5]);
+                acc[6] = fmaf(d1.z, xv, acc[6]); acc[7] = fmaf(d1.w, xv, acc[7]);
+            }
+            if (g == 0) acc[0] -= c00;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cc_s[r * cc_ld + 8 * g + i] = prm.mfcc_norm_factor * acc[i];
+        }
+    }
+    __syncthreads();
+    // ---- MFCC (+ delta, :226-228) output, clip (:238)
+    {
+        const int width = prm.use_delta ? 2 * n_mfcc : n_mfcc;
+        float* __restrict__ dst = mfcc_out + (rg.frame_off[u] + t0) * width;
+        const int n = nfr * width;
+        for (int e = tid; e < n; e += kFbThreads) {
+            const int r = e / width;
+            const int q = e - r * width;
+            const int t = t0 + r;
+            float v;
+            if (q < n_mfcc) {
+                v = cc_s[(r + 1) * cc_ld + q];
+            } else if (t == 0 || t == T - 1) {
+                v = 0.f;
+            } else {
+                v = 2.0f * (cc_s[(r + 2) * cc_ld + (q - n_mfcc)] - cc_s[r * cc_ld + (q - n_mfcc)]);
+            }
+            if (prm.clip) v = fminf(fmaxf(v, -1.f), 1.f);
+            dst[e] = v;
+        }
+    }
+}
+
+}  // namespace scdsp

@@ -1,0 +1,414 @@
+// Griffin-Lim kernels (fast path: n_fft = 400, hop = 80): griffin_lim_alg, audio_lib.py:249-274,
+// and the prologue / epilogue of from_power_to_wav, audio_lib.py:278-308.
+//
+// State between iterations is the WAVEFORM (float32, hop*(T-1) samples), not the complex
+// spectrogram: one launch of k_gl_iter does  wav -> reflect pad -> STFT -> A * X/|X| -> iSTFT ->
+// overlap-add -> / window-sum-square -> wav'  for a tile of 28 hops.  Each CTA recomputes the 4
+// halo frames it shares with its neighbours, so the overlap-add needs neither atomics nor a second
+// pass; per sample the covering frames are summed in ascending frame order like librosa.istft's loop.
+#pragma once
+#include "common.cuh"
+#include "fft400.cuh"
+
+namespace scdsp {
+
+constexpr int kGlFrames = 32;                          // frames per tile (16 units x 2)
+constexpr int kGlOutHops = kGlFrames - 4;              // complete hops per tile
+constexpr int kGlOut = kGlOutHops * kHop;              // 2240 output samples per tile
+constexpr int kGlSpan = kHop * (kGlFrames - 1) + 400;  // 2880
+constexpr int kGlSeg = 480;                            // samples written by one unit (2 frames)
+
+// one signal (utterance, or one rank's chunk of a long-form signal)
+struct GlJob {
+    int64_t amp_row0;     // row of frame `f_lo` in the amp / phase0 buffers
+    int64_t wav_in_off;   // element offset of this job's input waveform
+    int64_t wav_in_first; // whole-signal sample index of input element 0
+    int64_t wav_in_count; // input elements available
+    int64_t wav_out_off;  // element offset of output sample `out_first`
+    int64_t out_first;    // whole-signal index of the first sample to write
+    int64_t out_count;    // samples to write
+    int32_t f_lo, f_cnt;  // frames whose amp rows are present
+    int32_t T;            // frames of the whole signal
+    int32_t tile0;        // exclusive prefix of tiles
+};
+
+struct GlTables {
+    const float2* w400;
+    const float* win_half;     // 0.5 * hann (forward), centre padded to 400
+    const float* win_inv;      // hann / 400 (inverse)
+    const double* win_sq;      // hann^2 in float64 (window_sumsquare terms)
+    const float* inv_wss;      // steady-state 1 / sum-square, period = hop
+};
+
+// 1 / window_sumsquare at padded position p (librosa 0.6 filters.window_sumsquare, float32
+// accumulator receiving float64 terms in ascending frame order); 1 where the sum is <= tiny.
+__device__ __forceinline__ float inv_wss_at(int64_t p, int T, const GlTables& tb) {
+    int64_t lo = p >= kNfft ? (p - kNfft) / kHop + 1 : 0;
+    int64_t hi = p / kHop;
+    if (hi > T - 1) hi = T - 1;
+    if (hi - lo == kNfft / kHop - 1) return __ldg(tb.inv_wss + (int)(p % kHop));
+    float acc = 0.f;
+    for (int64_t i = lo; i <= hi; ++i) acc = (float)((double)acc + __ldg(tb.win_sq + (int)(p - i * kHop)));
+    return acc > 1.1754944e-38f ? 1.0f / acc : 1.0f;
+}
+
+struct GlSmem {
+    float span[kGlSpan];
+    float win_half[kNfft];
+    float win_inv[kNfft];
+    float2 slots[kFeUnits * kUnitSlots];   // reused as seg[16][480] floats after the inverse
+};
+
+template <bool INIT>
+__global__ void __launch_bounds__(kFeThreads, 2)
+k_gl_iter(const GlJob* __restrict__ jobs, int n_jobs, const int32_t* __restrict__ tile_prefix, GlTables tb,
+          const float* __restrict__ amp, const float* __restrict__ phase0, const float* __restrict__ wav_in,
+          float* __restrict__ wav_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GlSmem& sm = *reinterpret_cast<GlSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int ji = find_utt(tile_prefix, n_jobs, blockIdx.x);
+    const GlJob job = jobs[ji];
+    const int T = job.T;
+    const int64_t Lw = (int64_t)kHop * (T - 1);               // whole-signal length
+    // tiles sit on a whole-signal grid of kGlOut padded samples (padded = trimmed + 200), so a
+    // time-chunked run pairs and sums frames exactly like the unchunked one (bit-identical)
+    const int64_t p_first = ((job.out_first + kNfft / 2) / kGlOut) * kGlOut;
+    const int64_t o = p_first + (int64_t)(blockIdx.x - job.tile0) * kGlOut;
+    const int64_t t0 = o / kHop - 4;                           // first frame of the tile
+    const int64_t span0 = t0 * kHop;                           // padded position of span[0]
+
+    for (int i = tid; i < kNfft; i += kFeThreads) {
+        sm.win_half[i] = tb.win_half[i];
+        sm.win_inv[i] = tb.win_inv[i];
+    }
+    if (!INIT) {
+        const float* __restrict__ src = wav_in + job.wav_in_off;
+        for (int i = tid; i < kGlSpan; i += kFeThreads) {
+            const int64_t r = reflect_idx(span0 + i - kNfft / 2, Lw) - job.wav_in_first;
+            sm.span[i] = (r >= 0 && r < job.wav_in_count) ? __ldg(src + r) : 0.0f;
+        }
+    }
+    const int unit = tid / kUnitThreads;
+    const int j = tid - unit * kUnitThreads;
+    Twiddle tw;
+    load_twiddles(tw, tb.w400, j);
+    float2* unit_slots = sm.slots + unit * kUnitSlots;
+    __syncthreads();
+
+    if (!INIT) {
+        float s[24];
+        const float* __restrict__ src = sm.span + unit * (2 * kHop) + j;
+#pragma unroll
+        for (int m = 0; m < 24; ++m) s[m] = src[20 * m];
+        float2 z[20];
+#pragma unroll
+        for (int n1 = 0; n1 < 20; ++n1) {
+            const float w = sm.win_half[20 * n1 + j];
+            z[n1] = make_float2(s[n1] * w, s[n1 + 4] * w);
+        }
+        fwd_step1(z, tw, unit_slots + j);
+        __syncthreads();
+    }
+    // frames of this unit and their magnitude rows
+    const int64_t fa = t0 + 2 * unit, fb = fa + 1;
+    const bool va = fa >= job.f_lo && fa < (int64_t)job.f_lo + job.f_cnt && fa < T;
+    const bool vb = fb >= job.f_lo && fb < (int64_t)job.f_lo + job.f_cnt && fb < T;
+    {
+        const int64_t ra = job.amp_row0 + (va ? fa - job.f_lo : 0);
+        const int64_t rb = job.amp_row0 + (vb ? fb - job.f_lo : 0);
+        const float* __restrict__ amp_a = amp + ra * kBins;
+        const float* __restrict__ amp_b = amp + rb * kBins;
+        float2 v[20];
+        if (INIT) {
+            gl_init_state(v, j, amp_a, amp_b, phase0 + ra * kBins, phase0 + rb * kBins);
+        } else {
+            fwd_step2(v, unit_slots + j * kSlotLd);
+            gl_update(v, j, amp_a, amp_b);
+        }
+        inv_step2(v, unit_slots + j * kSlotLd);     // row j was read only by this thread
+    }
+    __syncthreads();
+    float comb[24];
+    {
+        float2 h[20];
+        inv_step1(h, tw, unit_slots + j);
+        const float ka = va ? 1.0f : 0.0f, kb = vb ? 1.0f : 0.0f;
+#pragma unroll
+        for (int m = 0; m < 24; ++m) {
+            float a = 0.f;
+            if (m < 20) a = h[m].x * (sm.win_inv[20 * m + j] * ka);
+            if (m >= 4) a += h[m - 4].y * (sm.win_inv[20 * (m - 4) + j] * kb);
+            comb[m] = a;
+        }
+    }
+    __syncthreads();                                 // every slot has been consumed
+    float* seg = reinterpret_cast<float*>(sm.slots);
+    {
+        float* __restrict__ dst = seg + unit * kGlSeg + j;
+#pragma unroll
+        for (int m = 0; m < 24; ++m) dst[20 * m] = comb[m];
+    }
+    __syncthreads();
+    // ---- ordered overlap-add gather + normalisation; local positions [320, 320 + kGlOut) are complete
+    {
+        float* __restrict__ dst = wav_out + job.wav_out_off;
+        const int64_t out_end = job.out_first + job.out_count;
+        for (int i = tid; i < kGlOut; i += kFeThreads) {
+            const int l = 320 + i;                                  // local padded offset in the tile
+            const int64_t p = span0 + l;                            // padded position
+            const int64_t s = p - kNfft / 2;                        // whole-signal sample index
+            if (s < job.out_first || s >= out_end || s >= Lw) continue;
+            int u_lo = l >= kGlSeg ? (l - kGlSeg) / (2 * kHop) + 1 : 0;
+            int u_hi = l / (2 * kHop);
+            if (u_hi > kFeUnits - 1) u_hi = kFeUnits - 1;
+            float acc = 0.f;
+            for (int uu = u_lo; uu <= u_hi; ++uu) acc += seg[uu * kGlSeg + (l - uu * 2 * kHop)];
+            dst[s - job.out_first] = acc * inv_wss_at(p, T, tb);
+        }
+    }
+}
+
+// sqrt(mean((a - b)^2)) per job: the value the reference prints when verbose (:262-264)
+__global__ void __launch_bounds__(256) k_rms_delta_partial(const float* __restrict__ a, const float* __restrict__ b,
+                                                          const GlJob* __restrict__ jobs, int n_jobs,
+                                                          const int32_t* __restrict__ prefix,
+                                                          double* __restrict__ partial) {
+    const int ji = find_utt(prefix, n_jobs, blockIdx.x);
+    const GlJob job = jobs[ji];
+    const int64_t begin = (int64_t)(blockIdx.x - prefix[ji]) * 8192;
+    const int64_t end = begin + 8192 < job.out_count ? begin + 8192 : job.out_count;
+    const float* __restrict__ pa = a + job.wav_out_off;
+    const float* __restrict__ pb = b + job.wav_out_off;
+    double s = 0.0;
+    for (int64_t i = begin + threadIdx.x; i < end; i += 256) {
+        const float d = pa[i] - pb[i];
+        s += (double)(d * d);
+    }
+    s = warp_sum(s);
+    __shared__ double red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        partial[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_rms_delta_final(const GlJob* __restrict__ jobs, int n_jobs,
+                                                        const int32_t* __restrict__ prefix,
+                                                        const double* __restrict__ partial, float* __restrict__ out,
+                                                        int n_iters, int iter) {
+    const int ji = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (ji >= n_jobs) return;
+    const int lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int t = prefix[ji] + lane; t < prefix[ji + 1]; t += 32) s += partial[t];
+    s = warp_sum(s);
+    if (lane == 0) out[(int64_t)ji * n_iters + iter] = (float)sqrt(s / (double)jobs[ji].out_count);
+}
+
+// ---------------------------------------------------------------------------------------------
+// from_power_to_wav prologue (:290-298)
+struct P2aJob {
+    int64_t row0;       // first row
+    int64_t rows;       // frames
+    int32_t tile0;
+    int32_t pad;
+};
+constexpr int kP2aChunk = 16384;   // elements per tile
+
+// partial sums of max(0,P) and max(0,P)^realse  (:293, :296)
+__global__ void __launch_bounds__(256) k_p2a_partial(const float* __restrict__ p, const P2aJob* __restrict__ jobs,
+                                                    int n_jobs, const int32_t* __restrict__ prefix, int bins,
+                                                    float realse, double* __restrict__ partial) {
+    const int ji = find_utt(prefix, n_jobs, blockIdx.x);
+    const P2aJob job = jobs[ji];
+    const int64_t n = job.rows * bins;
+    const int64_t begin = (int64_t)(blockIdx.x - prefix[ji]) * kP2aChunk;
+    const int64_t end = begin + kP2aChunk < n ? begin + kP2aChunk : n;
+    const float* __restrict__ src = p + job.row0 * bins;
+    double s0 = 0.0, s1 = 0.0;
+    for (int64_t i = begin + threadIdx.x; i < end; i += 256) {
+        const float v = fmaxf(src[i], 0.0f);
+        s0 += (double)v;
+        s1 += (double)powf(v, realse);
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1);
+    __shared__ double red[2][8];
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t0 = 0.0, t1 = 0.0;
+        for (int w = 0; w < 8; ++w) { t0 += red[0][w]; t1 += red[1][w]; }
+        partial[2 * blockIdx.x] = t0;
+        partial[2 * blockIdx.x + 1] = t1;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_p2a_scale(const P2aJob* __restrict__ jobs, int n_jobs,
+                                                  const int32_t* __restrict__ prefix,
+                                                  const double* __restrict__ partial, float* __restrict__ scale) {
+    const int ji = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (ji >= n_jobs) return;
+    const int lane = threadIdx.x & 31;
+    double s0 = 0.0, s1 = 0.0;
+    for (int t = prefix[ji] + lane; t < prefix[ji + 1]; t += 32) { s0 += partial[2 * t]; s1 += partial[2 * t + 1]; }
+    s0 = warp_sum(s0); s1 = warp_sum(s1);
+    // (p_mean / P.mean()) in float32 (:296); the element counts cancel
+    if (lane == 0) scale[ji] = (float)s0 / (float)s1;
+}
+
+__global__ void __launch_bounds__(256) k_p2a_apply(const float* __restrict__ p, const P2aJob* __restrict__ jobs,
+                                                  int n_jobs, const int32_t* __restrict__ prefix, int bins,
+                                                  float realse, int use_realse, const float* __restrict__ scale,
+                                                  float inv_norm, float* __restrict__ amp) {
+    const int ji = find_utt(prefix, n_jobs, blockIdx.x);
+    const P2aJob job = jobs[ji];
+    const int64_t n = job.rows * bins;
+    const int64_t begin = (int64_t)(blockIdx.x - prefix[ji]) * kP2aChunk;
+    const int64_t end = begin + kP2aChunk < n ? begin + kP2aChunk : n;
+    const float* __restrict__ src = p + job.row0 * bins;
+    float* __restrict__ dst = amp + job.row0 * bins;
+    const float sc = use_realse ? scale[ji] : 1.0f;
+    for (int64_t i = begin + threadIdx.x; i < end; i += 256) {
+        float v = fmaxf(src[i], 0.0f);
+        if (use_realse) v = sc * powf(v, realse);
+        const float db = v * inv_norm - 80.0f;                       // P / P_dB_norm_factor - 80
+        dst[i] = exp2f(0.16609640474436813f * db);                   // sqrt(10^(0.1*db)) = 2^(db*log2(10)/20)
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// from_power_to_wav epilogue (:301-306): de-emphasis IIR in float64 as a three-phase chunked scan,
+// then y * (m / mean|y|).
+constexpr int kIirChunk = 256;       // samples per thread-sequential chunk
+constexpr int kIirBlock = 128;       // chunks per block
+
+struct WavJob {
+    int64_t off;      // element offset
+    int64_t len;      // samples
+    int32_t tile0;    // prefix of blocks (kIirChunk * kIirBlock samples each)
+    int32_t chunk0;   // prefix of chunks
+};
+
+// phase 1: zero-state response at the end of each chunk
+__global__ void __launch_bounds__(kIirBlock) k_iir_local(const float* __restrict__ x, const WavJob* __restrict__ jobs,
+                                                        int n_jobs, const int32_t* __restrict__ prefix, double c,
+                                                        double* __restrict__ chunk_end) {
+    const int ji = find_utt(prefix, n_jobs, blockIdx.x);
+    const WavJob job = jobs[ji];
+    const int chunk = (blockIdx.x - prefix[ji]) * kIirBlock + threadIdx.x;
+    const int64_t begin = (int64_t)chunk * kIirChunk;
+    if (begin >= job.len) return;
+    const int64_t end = begin + kIirChunk < job.len ? begin + kIirChunk : job.len;
+    const float* __restrict__ src = x + job.off;
+    double y = 0.0;
+    for (int64_t i = begin; i < end; ++i) y = (double)src[i] + c * y;
+    chunk_end[job.chunk0 + chunk] = y;
+}
+
+// phase 2: carry into each chunk, sequential over the chunks of one signal (one thread per job)
+__global__ void __launch_bounds__(32) k_iir_carry(const WavJob* __restrict__ jobs, int n_jobs, double c,
+                                                 double* __restrict__ chunk_end) {
+    const int ji = blockIdx.x * 32 + threadIdx.x;
+    if (ji >= n_jobs) return;
+    const WavJob job = jobs[ji];
+    const int64_t n_chunks = (job.len + kIirChunk - 1) / kIirChunk;
+    double cl = 1.0;                                   // c^kIirChunk
+    for (int i = 0; i < kIirChunk; ++i) cl *= c;
+    double carry = 0.0;                                // state entering chunk k
+    for (int64_t k = 0; k < n_chunks; ++k) {
+        const double local = chunk_end[job.chunk0 + k];
+        chunk_end[job.chunk0 + k] = carry;             // overwrite with the incoming state
+        const int64_t len = (k + 1) * kIirChunk <= job.len ? kIirChunk : job.len - k * kIirChunk;
+        double cp = cl;
+        if (len != kIirChunk) { cp = 1.0; for (int64_t i = 0; i < len; ++i) cp *= c; }
+        carry = local + cp * carry;
+    }
+}
+
+// phase 3: rerun each chunk from its incoming state, write float64, accumulate |y| partials
+__global__ void __launch_bounds__(kIirBlock) k_iir_apply(const float* __restrict__ x, const WavJob* __restrict__ jobs,
+                                                        int n_jobs, const int32_t* __restrict__ prefix, double c,
+                                                        const double* __restrict__ chunk_in, double* __restrict__ out,
+                                                        double* __restrict__ abs_partial) {
+    const int ji = find_utt(prefix, n_jobs, blockIdx.x);
+    const WavJob job = jobs[ji];
+    const int chunk = (blockIdx.x - prefix[ji]) * kIirBlock + threadIdx.x;
+    const int64_t begin = (int64_t)chunk * kIirChunk;
+    double a = 0.0;
+    if (begin < job.len) {
+        const int64_t end = begin + kIirChunk < job.len ? begin + kIirChunk : job.len;
+        const float* __restrict__ src = x + job.off;
+        double* __restrict__ dst = out + job.off;
+        double y = chunk_in[job.chunk0 + chunk];
+        for (int64_t i = begin; i < end; ++i) {
+            y = (double)src[i] + c * y;
+            dst[i] = y;
+            a += fabs(y);
+        }
+    }
+    a = warp_sum(a);
+    __shared__ double red[kIirBlock / 32];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kIirBlock / 32; ++w) t += red[w];
+        abs_partial[blockIdx.x] = t;
+    }
+}
+
+// y *= m / mean|y|   (:306)
+__global__ void __launch_bounds__(256) k_renorm(const WavJob* __restrict__ jobs, int n_jobs,
+                                               const int32_t* __restrict__ prefix,
+                                               const double* __restrict__ abs_partial, double target,
+                                               double* __restrict__ out) {
+    const int ji = find_utt(prefix, n_jobs, blockIdx.x);
+    const WavJob job = jobs[ji];
+    __shared__ double scale_s;
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+        for (int t = prefix[ji] + threadIdx.x; t < prefix[ji + 1]; t += 32) s += abs_partial[t];
+        s = warp_sum(s);
+        if (threadIdx.x == 0) scale_s = target / (s / (double)job.len);
+    }
+    __syncthreads();
+    const double sc = scale_s;
+    const int64_t begin = (int64_t)(blockIdx.x - prefix[ji]) * (kIirChunk * kIirBlock);
+    const int64_t end = begin + kIirChunk * kIirBlock < job.len ? begin + kIirChunk * kIirBlock : job.len;
+    double* __restrict__ dst = out + job.off;
+    for (int64_t i = begin + threadIdx.x; i < end; i += 256) dst[i] *= sc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// standalone calc_preemphasis (:27): y[n] = x[n] - c*x[n-1], float64 out
+__global__ void __launch_bounds__(256) k_preemph(const float* __restrict__ x, int64_t n, double c,
+                                                double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const double prev = i > 0 ? (double)x[i - 1] : 0.0;
+    out[i] = (double)x[i] - c * prev;
+}
+
+// [rows][cols] -> [cols][rows] float32 (float64 or float32 source)
+template <typename T>
+__global__ void __launch_bounds__(256) k_transpose(const T* __restrict__ src, int64_t rows, int64_t cols,
+                                                  float* __restrict__ dst) {
+    __shared__ float tile[32][33];
+    const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int k = ty; k < 32; k += 8) {
+        const int64_t r = r0 + k, c = c0 + tx;
+        tile[k][tx] = (r < rows && c < cols) ? (float)src[r * cols + c] : 0.f;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int64_t c = c0 + k, r = r0 + tx;
+        if (c < cols && r < rows) dst[c * rows + r] = tile[tx][k];
+    }
+}
+
+}  // namespace scdsp

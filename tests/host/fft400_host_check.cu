@@ -1,0 +1,93 @@
+// CPU emulation of one FFT-400 "unit" (20 threads, one frame pair): runs the exact
+// __host__ __device__ routines of csrc/fft400.cuh thread by thread and compares them with a
+// naive float64 DFT.  Built and run by tests/test_host_fft400.py (no GPU needed).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../../speech_cloner_b200/csrc/fft400.cuh"
+
+using namespace scdsp;
+
+static void naive_rdft(const std::vector<double>& x, std::vector<double>& re, std::vector<double>& im) {
+    re.assign(kBins, 0.0); im.assign(kBins, 0.0);
+    for (int k = 0; k < kBins; ++k)
+        for (int n = 0; n < kNfft; ++n) {
+            const double a = -2.0 * M_PI * (double)((long)n * k % kNfft) / kNfft;
+            re[k] += x[n] * cos(a); im[k] += x[n] * sin(a);
+        }
+}
+
+int main() {
+    std::vector<float2> w400(kNfft);
+    for (int m = 0; m < kNfft; ++m) {
+        const double a = -2.0 * M_PI * m / kNfft;
+        w400[m] = make_float2((float)cos(a), (float)sin(a));
+    }
+    srand(7);
+    std::vector<double> xa(kNfft), xb(kNfft);
+    for (int n = 0; n < kNfft; ++n) {
+        xa[n] = (rand() / (double)RAND_MAX - 0.5) * (0.5 - 0.5 * cos(2 * M_PI * n / kNfft));
+        xb[n] = (rand() / (double)RAND_MAX - 0.5) * (0.5 - 0.5 * cos(2 * M_PI * n / kNfft)) + 0.3 * sin(0.31 * n);
+    }
+    std::vector<double> ar, ai, br, bi;
+    naive_rdft(xa, ar, ai); naive_rdft(xb, br, bi);
+
+    std::vector<float2> slots(kUnitSlots);
+    Twiddle tw[20];
+    for (int j = 0; j < 20; ++j) load_twiddles(tw[j], w400.data(), j);
+
+    // ---------------- forward + power
+    for (int j = 0; j < 20; ++j) {
+        float2 z[20];
+        for (int n1 = 0; n1 < 20; ++n1) z[n1] = make_float2(0.5f * (float)xa[20 * n1 + j], 0.5f * (float)xb[20 * n1 + j]);
+        fwd_step1(z, tw[j], &slots[j]);
+    }
+    std::vector<float> pa(kBins, -1.f), pb(kBins, -1.f);
+    float2 V[20][20];
+    for (int c = 0; c < 20; ++c) {
+        fwd_step2(V[c], &slots[c * kSlotLd]);
+        store_power(V[c], c, pa.data(), pb.data());
+    }
+    double pmax = 0, perr = 0;
+    for (int k = 0; k < kBins; ++k) {
+        const double ta = ar[k] * ar[k] + ai[k] * ai[k], tb = br[k] * br[k] + bi[k] * bi[k];
+        pmax = fmax(pmax, fmax(ta, tb));
+        perr = fmax(perr, fmax(fabs(pa[k] - ta), fabs(pb[k] - tb)));
+    }
+    printf("power max %.4g  max abs err %.3g  rel %.3g\n", pmax, perr, perr / pmax);
+    int fail = perr / pmax > 2e-6;
+
+    // ---------------- forward -> gl_update with A = |X| (identity) -> inverse == input
+    std::vector<float> ampa(kBins), ampb(kBins), pha(kBins), phb(kBins);
+    for (int k = 0; k < kBins; ++k) {
+        ampa[k] = (float)hypot(ar[k], ai[k]); ampb[k] = (float)hypot(br[k], bi[k]);
+        pha[k] = (float)atan2(ai[k], ar[k]); phb[k] = (float)atan2(bi[k], br[k]);
+    }
+    for (int mode = 0; mode < 2; ++mode) {
+        for (int c = 0; c < 20; ++c) {
+            float2 u[20];
+            if (mode == 0) {
+                for (int i = 0; i < 20; ++i) u[i] = V[c][i];
+                gl_update(u, c, ampa.data(), ampb.data());
+            } else {
+                gl_init_state(u, c, ampa.data(), ampb.data(), pha.data(), phb.data());
+            }
+            inv_step2(u, &slots[c * kSlotLd]);
+        }
+        double rerr = 0, xmax = 0;
+        for (int j = 0; j < 20; ++j) {
+            float2 h[20];
+            inv_step1(h, tw[j], &slots[j]);
+            for (int n1 = 0; n1 < 20; ++n1) {
+                rerr = fmax(rerr, fabs(h[n1].x / 400.0 - xa[20 * n1 + j]));
+                rerr = fmax(rerr, fabs(h[n1].y / 400.0 - xb[20 * n1 + j]));
+                xmax = fmax(xmax, fmax(fabs(xa[20 * n1 + j]), fabs(xb[20 * n1 + j])));
+            }
+        }
+        printf("mode %d roundtrip max abs err %.3g (signal max %.3g)\n", mode, rerr, xmax);
+        fail |= rerr / xmax > 5e-6;
+    }
+    printf(fail ? "FAIL\n" : "OK\n");
+    return fail;
+}

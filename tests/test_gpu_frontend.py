@@ -1,0 +1,142 @@
+"""GPU parity of the front-end (calc_MFCC_input, /root/reference/audio_lib.py:89-244) against the oracle.
+
+Tolerance (BASELINE.json north_star): 1e-4 relative / 1e-5 absolute on all three float32 outputs.
+Every call goes through the C ABI of include/speechdsp.h via speech_cloner_b200.audio_lib.
+"""
+import numpy as np
+import pytest
+
+from oracle import audio_lib_oracle as oracle
+from speech_cloner_b200 import synth
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+HP = dict(synth.HP_ENC)
+
+
+@pytest.fixture(scope="module")
+def al(built_lib):
+    from speech_cloner_b200 import audio_lib
+    return audio_lib
+
+
+def _check(al, y, what, **kw):
+    got = al.calc_MFCC_input(y, **kw)
+    want = oracle.calc_MFCC_input(y, **kw)
+    for g, w, name in zip(got, want, ("MFCC", "M_dB", "P_dB")):
+        assert g.dtype == np.float32 and g.flags["C_CONTIGUOUS"]
+        assert_close(g, w, what=f"{what}/{name}")
+
+
+def test_single_utterance_hp(al):
+    _check(al, synth.utterance(1000, 3.0, ds_norm=(0.0, 10.0)), "hp 3s", **HP)
+
+
+def test_config1_batch_32x3s(al):
+    """BASELINE.json configs[0]: 32 synthetic 16 kHz 3 s TIMIT-shaped utterances at hp/ds_enc_cfg_d.json."""
+    wavs = synth.batch(1, 32, 3.0, ds_norm=(0.0, 10.0))
+    got = al.calc_MFCC_input_batch(wavs, **HP)
+    assert len(got) == 32
+    for i, (y, g) in enumerate(zip(wavs, got)):
+        want = oracle.calc_MFCC_input(y, **HP)
+        assert g[0].shape == (601, 80) and g[1].shape == (601, 80) and g[2].shape == (601, 201)
+        for a, b, name in zip(g, want, ("MFCC", "M_dB", "P_dB")):
+            assert_close(a, b, what=f"utt {i}/{name}")
+
+
+def test_ragged_batch_equals_single_calls(al):
+    lens = [48000, 16001, 7999, 400, 399, 81, 80, 160, 33333]
+    wavs = [synth.utterance(50 + i, n / 16000.0)[:n] for i, n in enumerate(lens)]
+    got = al.calc_MFCC_input_batch(wavs, **HP)
+    for y, g in zip(wavs, got):
+        single = al.calc_MFCC_input(y, **HP)
+        want = oracle.calc_MFCC_input(y, **HP)
+        for a, s, w in zip(g, single, want):
+            assert a.shape == w.shape == s.shape
+            np.testing.assert_array_equal(a, s)          # batching must not change a bit
+            assert_close(a, w, what=f"len {len(y)}")
+
+
+@pytest.mark.parametrize("case", ["noise", "sine_on_bin", "sine_between_bins", "impulse", "leading_zeros", "short"])
+def test_adversarial_inputs(al, case):
+    rng = np.random.default_rng(7)
+    n = 16000
+    t = np.arange(n) / 16000.0
+    if case == "noise":
+        y = 0.1 * rng.standard_normal(n)
+    elif case == "sine_on_bin":
+        y = 0.1 * np.sin(2 * np.pi * 1000.0 * t) + 1e-4 * rng.standard_normal(n)
+    elif case == "sine_between_bins":
+        y = 0.1 * np.sin(2 * np.pi * 1020.0 * t) + 1e-4 * rng.standard_normal(n)
+    elif case == "impulse":
+        y = 1e-4 * rng.standard_normal(n); y[5000] = 0.5
+    elif case == "leading_zeros":
+        y = 0.05 * rng.standard_normal(n); y[:4000] = 0.0
+    else:
+        y = 0.1 * rng.standard_normal(250)                   # L < n_fft: reflect pad wraps more than once
+    _check(al, y.astype(np.float32), case, **HP)
+
+
+@pytest.mark.parametrize("override", [
+    dict(calc_mfcc_derivate=False),
+    dict(mfcc_normaleze_first_mfcc=False),
+    dict(clip_output=False),
+    dict(pre_emphasis=0.0),
+    dict(mean_abs_amp_norm=1.0),
+    dict(P_dB_norm_factor=1.0, M_dB_norm_factor=1.0, mfcc_norm_factor=1.0, clip_output=False),
+    dict(window="hamming"),
+    dict(win_length=320, n_fft=400),
+    dict(n_mels=128, n_mfcc=20),
+    dict(n_mels=40, n_mfcc=13, sr=8000),
+])
+def test_parameter_switches(al, override):
+    kw = dict(HP); kw.update(override)
+    tol = {}
+    _check(al, synth.utterance(77, 1.5), str(override), **kw)
+
+
+@pytest.mark.parametrize("geom", [
+    dict(hop_length=40, win_length=400, n_mels=128),           # calc_MFCC_input's own defaults (:92-94)
+    dict(hop_length=128, win_length=512, n_fft=512),
+    dict(hop_length=100, win_length=300, n_fft=384, window="hamming"),
+])
+def test_generic_geometry(al, geom):
+    kw = dict(HP); kw.update(geom)
+    _check(al, synth.utterance(78, 1.0), str(geom), **kw)
+
+
+def test_invalid_inputs_raise(al):
+    with pytest.raises(ValueError):
+        al.calc_MFCC_input([0.0, 1.0], **HP)
+    with pytest.raises(ValueError):
+        al.calc_MFCC_input(np.zeros(100, dtype=np.int16), **HP)
+    with pytest.raises(ValueError):
+        al.calc_MFCC_input(np.zeros((2, 100), dtype=np.float32), **HP)
+    y = np.ones(1000, dtype=np.float32); y[3] = np.nan
+    with pytest.raises(ValueError):
+        al.calc_MFCC_input(y, **HP)
+    with pytest.raises(ValueError):
+        al.calc_MFCC_input(np.ones(40, dtype=np.float32), **HP)      # 1 frame + delta -> reference raises too
+
+
+def test_device_tensor_in_out(al):
+    import torch
+    y = synth.utterance(5, 2.0)
+    want = oracle.calc_MFCC_input(y, **HP)
+    got = al.calc_MFCC_input(torch.from_numpy(y).cuda(), **HP)
+    for g, w in zip(got, want):
+        assert g.is_cuda
+        assert_close(g.cpu().numpy(), w)
+
+
+def test_preemphasis_pair(al):
+    y = synth.utterance(9, 1.0)
+    pe = al.calc_preemphasis(y, 0.97)
+    assert pe.dtype == np.float64
+    np.testing.assert_allclose(pe, oracle.calc_preemphasis(y, 0.97), rtol=0, atol=1e-12)
+    inv = al.calc_inv_preemphasis(y, 0.97)
+    assert inv.dtype == np.float64
+    np.testing.assert_allclose(inv, oracle.calc_inv_preemphasis(y, 0.97), rtol=1e-12, atol=1e-13)
+    # round trip through both filters recovers the float32 signal
+    np.testing.assert_allclose(al.calc_inv_preemphasis(pe.astype(np.float32), 0.97), y, atol=2e-6)
