@@ -25,7 +25,7 @@ class ScParams(C.Structure):
         ("sample_rate", C.c_int32), ("n_fft", C.c_int32), ("win_length", C.c_int32),
         ("hop_length", C.c_int32), ("n_mels", C.c_int32), ("n_mfcc", C.c_int32),
         ("mfcc_normalize_first", C.c_int32), ("calc_mfcc_derivative", C.c_int32),
-        ("clip_output", C.c_int32), ("reserved0", C.c_int32),
+        ("clip_output", C.c_int32), ("fft_precision", C.c_int32),
         ("pre_emphasis", C.c_double), ("mfcc_norm_factor", C.c_double),
         ("m_db_norm_factor", C.c_double), ("p_db_norm_factor", C.c_double),
         ("mean_abs_amp_norm", C.c_double),
@@ -47,6 +47,7 @@ PROTOTYPES = {
     "sc_plan_is_fast_path": (C.c_int, [_P]),
     "sc_num_frames": (C.c_int64, [_P, C.c_int64]),
     "sc_frontend_batch": (C.c_int, [_P, _P, _I64P, _I64P, C.c_int32, _P, _P, _P, _I64P, _P]),
+    "sc_mean_abs_batch": (C.c_int, [_P, _P, _I64P, _I64P, C.c_int32, _P, _P]),
     "sc_preemphasis": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P]),
     "sc_inv_preemphasis": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P]),
     "sc_power_to_amp_batch": (C.c_int, [_P, _P, _I64P, _I64P, C.c_int32, C.c_double, C.c_double, _P, _P]),

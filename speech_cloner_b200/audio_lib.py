@@ -63,7 +63,7 @@ class DspPlan:
     def __init__(self, sr=16000, n_fft=400, win_length=400, hop_length=80, n_mels=80, n_mfcc=40,
                  window="hann", pre_emphasis=0.97, mfcc_normaleze_first_mfcc=True, mfcc_norm_factor=0.01,
                  calc_mfcc_derivate=False, M_dB_norm_factor=0.01, P_dB_norm_factor=0.01,
-                 mean_abs_amp_norm=0.003, clip_output=True):
+                 mean_abs_amp_norm=0.003, clip_output=True, fft_precision="fp64"):
         lib = _lib.load()
         _require_cuda()
         if n_fft is None:
@@ -75,6 +75,9 @@ class DspPlan:
         prm.mfcc_normalize_first = int(bool(mfcc_normaleze_first_mfcc))
         prm.calc_mfcc_derivative = int(bool(calc_mfcc_derivate))
         prm.clip_output = int(bool(clip_output))
+        if fft_precision not in ("fp64", "fp32"):
+            raise ValueError("fft_precision must be 'fp64' or 'fp32'")
+        prm.fft_precision = 1 if fft_precision == "fp32" else 0
         prm.pre_emphasis = float(pre_emphasis); prm.mfcc_norm_factor = float(mfcc_norm_factor)
         prm.m_db_norm_factor = float(M_dB_norm_factor); prm.p_db_norm_factor = float(P_dB_norm_factor)
         prm.mean_abs_amp_norm = float(mean_abs_amp_norm)
@@ -192,9 +195,25 @@ def frontend_device(plan: DspPlan, wav_dev, layout: FrontendLayout, out=None):
     return out
 
 
+FFT_PRECISION = "fp64"
+"""Front-end FFT arithmetic used by the reference-signature functions: ``"fp64"`` reproduces the
+reference's float64 scipy FFT to the 1e-4/1e-5 tolerance everywhere; ``"fp32"`` is faster but bins
+70-80 dB below the utterance maximum can deviate by up to ~5e-5 (documented in DESIGN.md)."""
+
+
+def mean_abs_device(plan: DspPlan, wav_dev, layout: FrontendLayout):
+    """float32 ``np.abs(y).mean()`` per utterance (bit-identical to NumPy), as a CUDA tensor."""
+    torch = _require_cuda()
+    out = torch.empty(len(layout.lengths), dtype=torch.float32, device="cuda")
+    _lib.check(plan._lib.sc_mean_abs_batch(plan._h, wav_dev.data_ptr(), layout.c_sample_offsets,
+                                           layout.c_sample_lengths, len(layout.lengths), out.data_ptr(),
+                                           _stream_ptr(torch)), "sc_mean_abs_batch")
+    return out
+
+
 def _plan_from_kwargs(sr, pre_emphasis, hop_length, win_length, n_mels, n_mfcc, n_fft, window,
                       mfcc_normaleze_first_mfcc, mfcc_norm_factor, calc_mfcc_derivate, M_dB_norm_factor,
-                      P_dB_norm_factor, mean_abs_amp_norm, clip_output) -> DspPlan:
+                      P_dB_norm_factor, mean_abs_amp_norm, clip_output, fft_precision=None) -> DspPlan:
     if n_fft is None:
         n_fft = win_length
     return DspPlan.get(sr=sr, n_fft=int(n_fft), win_length=int(win_length), hop_length=int(hop_length),
@@ -202,13 +221,15 @@ def _plan_from_kwargs(sr, pre_emphasis, hop_length, win_length, n_mels, n_mfcc, 
                        mfcc_normaleze_first_mfcc=bool(mfcc_normaleze_first_mfcc),
                        mfcc_norm_factor=float(mfcc_norm_factor), calc_mfcc_derivate=bool(calc_mfcc_derivate),
                        M_dB_norm_factor=float(M_dB_norm_factor), P_dB_norm_factor=float(P_dB_norm_factor),
-                       mean_abs_amp_norm=float(mean_abs_amp_norm), clip_output=bool(clip_output))
+                       mean_abs_amp_norm=float(mean_abs_amp_norm), clip_output=bool(clip_output),
+                       fft_precision=fft_precision or FFT_PRECISION)
 
 
 def calc_MFCC_input_batch(wavs, sr=16000, pre_emphasis=0.97, hop_length=40, win_length=400, n_mels=128,
                           n_mfcc=40, n_fft=None, window='hann', mfcc_normaleze_first_mfcc=True,
                           mfcc_norm_factor=0.01, calc_mfcc_derivate=False, M_dB_norm_factor=0.01,
-                          P_dB_norm_factor=0.01, mean_abs_amp_norm=0.003, clip_output=True, return_device=False):
+                          P_dB_norm_factor=0.01, mean_abs_amp_norm=0.003, clip_output=True, return_device=False,
+                          fft_precision=None):
     """``calc_MFCC_input`` over a list of waveforms as ONE ragged GPU batch.
 
     Returns a list of ``(MFCC, M_dB, P_dB)`` triples (NumPy views of three packed host arrays, or
@@ -225,7 +246,7 @@ def calc_MFCC_input_batch(wavs, sr=16000, pre_emphasis=0.97, hop_length=40, win_
     torch = _require_cuda()
     plan = _plan_from_kwargs(sr, pre_emphasis, hop_length, win_length, n_mels, n_mfcc, n_fft, window,
                              mfcc_normaleze_first_mfcc, mfcc_norm_factor, calc_mfcc_derivate, M_dB_norm_factor,
-                             P_dB_norm_factor, mean_abs_amp_norm, clip_output)
+                             P_dB_norm_factor, mean_abs_amp_norm, clip_output, fft_precision)
     layout = FrontendLayout([int(w.shape[0]) for w in wavs], plan.hop_length)
     if device_in:
         wav_dev = torch.zeros(layout.total_samples, dtype=torch.float32, device="cuda")

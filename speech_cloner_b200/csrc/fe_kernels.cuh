@@ -15,8 +15,10 @@
 namespace scdsp {
 
 struct FeTables {
-    const float2* w400;        // W400^m = exp(-2*pi*i*m/400), m in [0, 400)
+    const cxf* w400;           // W400^m = exp(-2*pi*i*m/400), m in [0, 400)
     const float* win_half;     // 0.5 * analysis window, centre padded to 400
+    const cxd* w400_d;         // the same two tables in float64 (default, reference-exact FFT)
+    const double* win_half_d;
     const float2* mel_w;       // per bin: (weight into band i(k), weight into band i(k)-1)
     const int32_t* mel_istart; // first bin of mel interval i, i in [0, n_mels + 1]; [n_mels+1] = bins
     const int32_t* mel_chunk;  // band boundaries of the kMaxMelChunks work chunks
@@ -36,46 +38,118 @@ struct FeParams {
 };
 
 // ---------------------------------------------------------------------------------------------
-// mean|y| : per-(utterance, chunk) float64 partial sums, then one warp per utterance adds them in
-// a fixed order (deterministic) and writes the gain.
-constexpr int kAbsChunk = 8192;
+// mean|y| (audio_lib.py:126) must equal NumPy's float32 result BIT FOR BIT: the reference multiplies
+// every sample by the float32 gain, and a gain that is one ulp off re-rounds all of them, which moves
+// bins near the top_db floor by up to 3e-5 (measured) - more than the 1e-5 tolerance.  NumPy sums a
+// contiguous float32 array with this fixed recursive tree (numpy/_core/src/umath/loops_utils.h.src):
+//   n <= 128 : 8 strided accumulators r[j] += a[i+j], res = ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)),
+//              then the n % 8 tail added one by one          (n < 8: plain left-to-right sum)
+//   n >  128 : n2 = n/2 rounded down to a multiple of 8;  sum(a[:n2]) + sum(a[n2:])
+// The tree depends only on n.  Each CTA owns the subtree `idx` at depth D (D chosen on the host so
+// that a subtree has <= kAbsSubtree samples), expands it into a 255-node heap in shared memory,
+// reduces the leaves with 8-lane groups and folds the heap bottom-up; k_gain_finalize folds the top
+// D levels.  Verified bitwise against numpy in tests/test_gpu_frontend.py::test_gain_matches_numpy.
+constexpr int kAbsSubtree = 8000;
+constexpr int kAbsThreads = 256;
 
-__global__ void __launch_bounds__(256) k_abs_partial(const float* __restrict__ wav, Ragged rg,
-                                                     double* __restrict__ partial) {
-    const int tile = blockIdx.x;
-    const int u = find_utt(rg.tile_prefix, rg.n_utts, tile);
-    const int64_t begin = (int64_t)(tile - rg.tile_prefix[u]) * kAbsChunk;
-    const int64_t len = rg.sample_len[u];
-    const int64_t end = begin + kAbsChunk < len ? begin + kAbsChunk : len;
-    const float* __restrict__ y = wav + rg.sample_off[u];
-    double s = 0.0;
-    for (int64_t i = begin + threadIdx.x; i < end; i += 256) s += (double)fabsf(__ldg(y + i));
-    s = warp_sum(s);
-    __shared__ double red[8];
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) t += red[w];
-        partial[tile] = t;
-    }
+__host__ __device__ inline int abs_depth(int64_t n) {
+    int d = 0;
+    while ((n >> d) > kAbsSubtree) ++d;
+    return d;
 }
 
-__global__ void __launch_bounds__(128) k_gain_finalize(Ragged rg, const double* __restrict__ partial,
-                                                       UttStat* __restrict__ stat, double mean_abs_amp_norm,
-                                                       int use_gain) {
+__global__ void __launch_bounds__(kAbsThreads) k_abs_pairwise(const float* __restrict__ wav, Ragged rg,
+                                                              const int64_t* __restrict__ heap_off,
+                                                              float* __restrict__ heap) {
+    __shared__ int hs[256];
+    __shared__ int hn[256];
+    __shared__ float hv[256];
+    const int tid = threadIdx.x;
+    const int u = find_utt(rg.tile_prefix, rg.n_utts, blockIdx.x);
+    const int idx = blockIdx.x - rg.tile_prefix[u];
+    const int64_t len = rg.sample_len[u];
+    const int D = abs_depth(len);
+    int64_t start = 0, n = len;
+    for (int b = D - 1; b >= 0; --b) {
+        int64_t n2 = n / 2;
+        n2 -= n2 % 8;
+        if ((idx >> b) & 1) { start += n2; n -= n2; } else { n = n2; }
+    }
+    const float* __restrict__ a = wav + rg.sample_off[u] + start;
+    if (tid == 0) { hs[1] = 0; hn[1] = (int)n; }
+    __syncthreads();
+    for (int l = 0; l < 7; ++l) {
+        if (tid < (1 << l)) {
+            const int i = (1 << l) + tid;
+            const int m = hn[i];
+            if (m > 128) {
+                int n2 = m / 2;
+                n2 -= n2 % 8;
+                hs[2 * i] = hs[i]; hn[2 * i] = n2;
+                hs[2 * i + 1] = hs[i] + n2; hn[2 * i + 1] = m - n2;
+            } else {
+                hn[2 * i] = 0; hn[2 * i + 1] = 0;
+            }
+        }
+        __syncthreads();
+    }
+    // leaves: one 8-lane group per node
+    {
+        const int g = tid >> 3, j = tid & 7;
+        const unsigned gmask = 0xffu << (8 * ((tid & 31) >> 3));     // the 8 lanes of this group only
+        for (int i = 1 + g; i < 256; i += kAbsThreads / 8) {
+            const int m = hn[i];
+            if (m <= 0 || m > 128) continue;
+            const float* __restrict__ p = a + hs[i];
+            float res;
+            if (m < 8) {
+                res = 0.f;
+                for (int k = 0; k < m; ++k) res += fabsf(__ldg(p + k));
+            } else {
+                float r = fabsf(__ldg(p + j));
+                const int body = m - (m % 8);
+                for (int k = 8; k < body; k += 8) r += fabsf(__ldg(p + k + j));
+                r += __shfl_xor_sync(gmask, r, 1, 8);
+                r += __shfl_xor_sync(gmask, r, 2, 8);
+                r += __shfl_xor_sync(gmask, r, 4, 8);
+                res = r;
+                for (int k = body; k < m; ++k) res += fabsf(__ldg(p + k));
+            }
+            if (j == 0) hv[i] = res;
+        }
+    }
+    __syncthreads();
+    for (int l = 6; l >= 0; --l) {
+        if (tid < (1 << l)) {
+            const int i = (1 << l) + tid;
+            if (hn[i] > 128) hv[i] = hv[2 * i] + hv[2 * i + 1];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) heap[heap_off[u] + (1 << D) + idx] = hv[1];
+}
+
+__global__ void __launch_bounds__(128) k_gain_finalize(Ragged rg, const int64_t* __restrict__ heap_off,
+                                                       float* __restrict__ heap, UttStat* __restrict__ stat,
+                                                       double mean_abs_amp_norm, int use_gain,
+                                                       float* __restrict__ mean_out) {
     const int u = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (u >= rg.n_utts) return;
     const int lane = threadIdx.x & 31;
     float gain = 1.0f;
     if (use_gain) {
-        double s = 0.0;
-        for (int t = rg.tile_prefix[u] + lane; t < rg.tile_prefix[u + 1]; t += 32) s += partial[t];
-        s = warp_sum(s);
-        // np.abs(y).mean() is a float32; python float / float32 was a float64 in the reference era
-        const float mean32 = (float)(s / (double)rg.sample_len[u]);
+        const int64_t len = rg.sample_len[u];
+        const int D = abs_depth(len);
+        volatile float* h = heap + heap_off[u];
+        for (int l = D - 1; l >= 0; --l) {
+            for (int i = (1 << l) + lane; i < (2 << l); i += 32) h[i] = h[2 * i] + h[2 * i + 1];
+            __threadfence_block();
+            __syncwarp();
+        }
+        // np.abs(y).mean(): float32 sum / n in float32; python float / float32 -> float64 (reference era)
+        const float mean32 = __fdiv_rn(h[1], (float)len);
         gain = (float)(mean_abs_amp_norm / (double)mean32);
+        if (mean_out && lane == 0) mean_out[u] = mean32;
     }
     if (lane == 0) {
         UttStat st;
@@ -166,10 +240,17 @@ __device__ __forceinline__ void fe_epilogue_a(const float* __restrict__ power, i
 
 // ---------------------------------------------------------------------------------------------
 // Pass A.  One CTA = 32 consecutive frames of one utterance = 16 units x 20 threads.
+// R = double (default): float64 butterflies like the reference's scipy FFT (audio_lib.py:141-147,
+// float64 window * float64 pre-emphasised samples), R = float: opt-in fast mode.
+template <typename R> struct FeTw { using type = TwReg<float>; };
+template <> struct FeTw<double> { using type = TwTab<double>; };
+
+template <typename R>
 struct FeSmemA {
-    float span[kFeSpan];                       // pre-emphasised, reflect-padded samples of the tile
-    float win[kNfft];
-    float2 slots[kFeUnits * kUnitSlots];       // step-1 -> step-2 exchange
+    R span[kFeSpan];                           // pre-emphasised, reflect-padded samples of the tile
+    R win[kNfft];
+    cx<R> slots[kFeUnits * kUnitSlots];        // step-1 -> step-2 exchange
+    cx<R> w400[sizeof(R) == 8 ? kNfft : 1];    // twiddle table (float64 path reads it on use)
     float power[kFeFrames * kBins];            // |X|^2, row = frame
     float2 mel_w[kBins];
     int32_t mel_istart[kMaxMels + 2];
@@ -177,12 +258,14 @@ struct FeSmemA {
     // followed by mel_db[kFeFrames][n_mels + 1]
 };
 
-__global__ void __launch_bounds__(kFeThreads, 2)
+template <typename R>
+__global__ void __launch_bounds__(kFeThreads, sizeof(R) == 8 ? 1 : 2)
 k_fe_pass_a(const float* __restrict__ wav, Ragged rg, FeTables tb, FeParams prm, UttStat* __restrict__ stat,
             float* __restrict__ pdb_out, float* __restrict__ mel_raw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    FeSmemA& sm = *reinterpret_cast<FeSmemA*>(smem_raw);
-    float* mel_db = reinterpret_cast<float*>(smem_raw + sizeof(FeSmemA));
+    FeSmemA<R>& sm = *reinterpret_cast<FeSmemA<R>*>(smem_raw);
+    float* mel_db = reinterpret_cast<float*>(smem_raw + sizeof(FeSmemA<R>));
+    constexpr bool kF64 = sizeof(R) == 8;
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
     const int u = find_utt(rg.tile_prefix, rg.n_utts, tile);
@@ -202,37 +285,45 @@ k_fe_pass_a(const float* __restrict__ wav, Ragged rg, FeTables tb, FeParams prm,
             const int64_t r = reflect_idx(q0 + i, L);
             const float cur = gain * __ldg(y + r);
             const float prev = r > 0 ? gain * __ldg(y + r - 1) : 0.0f;
-            sm.span[i] = (float)((double)cur - c * (double)prev);
+            sm.span[i] = (R)((double)cur - c * (double)prev);
         }
-        for (int i = tid; i < kNfft; i += kFeThreads) sm.win[i] = tb.win_half[i];
+        if (kF64) {
+            for (int i = tid; i < kNfft; i += kFeThreads) {
+                sm.win[i] = (R)tb.win_half_d[i];
+                sm.w400[i] = mk<R>((R)tb.w400_d[i].x, (R)tb.w400_d[i].y);
+            }
+        } else {
+            for (int i = tid; i < kNfft; i += kFeThreads) sm.win[i] = (R)tb.win_half[i];
+        }
         for (int i = tid; i < kBins; i += kFeThreads) sm.mel_w[i] = tb.mel_w[i];
         for (int i = tid; i < n_mels + 2; i += kFeThreads) sm.mel_istart[i] = tb.mel_istart[i];
     }
     const int unit = tid / kUnitThreads;
     const int j = tid - unit * kUnitThreads;
-    Twiddle tw;
-    load_twiddles(tw, tb.w400, j);
+    typename FeTw<R>::type tw;
+    if (kF64) tw.load(reinterpret_cast<const cx<R>*>(sm.w400), j);
+    else tw.load(reinterpret_cast<const cx<R>*>(tb.w400), j);
     __syncthreads();
 
     // ---- step 1: frames A = 2*unit, B = A + 1 share 24 strided samples (hop = 4 * 20)
-    float2* unit_slots = sm.slots + unit * kUnitSlots;
+    cx<R>* unit_slots = sm.slots + unit * kUnitSlots;
     {
-        float s[24];
-        const float* __restrict__ src = sm.span + unit * (2 * kHop) + j;
+        R s[24];
+        const R* __restrict__ src = sm.span + unit * (2 * kHop) + j;
 #pragma unroll
         for (int m = 0; m < 24; ++m) s[m] = src[20 * m];
-        float2 z[20];
+        cx<R> z[20];
 #pragma unroll
         for (int n1 = 0; n1 < 20; ++n1) {
-            const float w = sm.win[20 * n1 + j];
-            z[n1] = make_float2(s[n1] * w, s[n1 + 4] * w);
+            const R w = sm.win[20 * n1 + j];
+            z[n1] = mk<R>(s[n1] * w, s[n1 + 4] * w);
         }
         fwd_step1(z, tw, unit_slots + j);
     }
     __syncthreads();
     // ---- step 2 + |X|^2
     {
-        float2 v[20];
+        cx<R> v[20];
         fwd_step2(v, unit_slots + j * kSlotLd);
         float* pa = sm.power + (2 * unit) * kBins;
         store_power(v, j, pa, pa + kBins);

@@ -24,15 +24,13 @@
 #pragma once
 #include "dft20.cuh"
 
-#define SC_HD __host__ __device__ __forceinline__
-
 namespace scdsp {
 
 constexpr int kNfft = 400;            // fast-path FFT length
 constexpr int kBins = 201;            // 1 + kNfft/2
 constexpr int kUnitThreads = 20;      // threads per unit (one frame pair)
-constexpr int kSlotLd = 21;           // slot row stride (float2), odd => conflict-free both ways
-constexpr int kUnitSlots = 20 * kSlotLd;  // 420 float2 per unit
+constexpr int kSlotLd = 21;           // slot row stride (complex), odd => conflict-free both ways
+constexpr int kUnitSlots = 20 * kSlotLd;  // 420 complex per unit
 
 SC_HD float sc_rsqrt(float x) {
 #ifdef __CUDA_ARCH__
@@ -42,35 +40,50 @@ SC_HD float sc_rsqrt(float x) {
 #endif
 }
 
-// Per-thread twiddles: tw[k1] = W400^(j*k1) for k1 = 1..9, tw[0] = W400^(10*j).
-struct Twiddle {
-    float2 tw[10];
-};
-
-SC_HD void load_twiddles(Twiddle& t, const float2* __restrict__ w400, int j) {
+// Per-thread twiddles W400^(j*k1), k1 = 1..9, and W400^(10*j).
+// TwReg keeps them in registers (float32 kernels); TwTab reads a (shared-memory) table on use
+// (float64 front-end, where 19 complex doubles would cost 76 registers).
+template <typename R> struct TwReg {
+    cx<R> tw[10];
+    SC_HD void load(const cx<R>* __restrict__ w400, int j) {
 #pragma unroll
-    for (int k1 = 1; k1 < 10; ++k1) t.tw[k1] = w400[j * k1];
-    t.tw[0] = w400[10 * j];
-}
+        for (int k1 = 1; k1 < 10; ++k1) tw[k1] = w400[j * k1];
+        tw[0] = w400[10 * j];
+    }
+    SC_HD cx<R> get(int k1) const { return tw[k1]; }
+    SC_HD cx<R> get10() const { return tw[0]; }
+};
+template <typename R> struct TwTab {
+    const cx<R>* tab;
+    int j;
+    SC_HD void load(const cx<R>* w400, int j_) { tab = w400; j = j_; }
+    SC_HD cx<R> get(int k1) const { return tab[j * k1]; }
+    SC_HD cx<R> get10() const { return tab[10 * j]; }
+};
+using Twiddle = TwReg<float>;
+SC_HD void load_twiddles(Twiddle& t, const cxf* __restrict__ w400, int j) { t.load(w400, j); }
 
 // ---- forward step 1: z[n1] = 0.5*w*(xA, xB) at sample 20*n1 + j  ->  slot column j
-SC_HD void fwd_step1(float2 (&z)[20], const Twiddle& t, float2* __restrict__ slot_col) {
+template <typename R, typename TW>
+SC_HD void fwd_step1(cx<R> (&z)[20], const TW& t, cx<R>* __restrict__ slot_col) {
     dft20<false>(z);
-    slot_col[0] = make_float2(z[0].x + z[0].x, z[0].y + z[0].y);
-    const float2 z10 = make_float2(z[10].x + z[10].x, z[10].y + z[10].y);
-    slot_col[10 * kSlotLd] = cmul(z10, t.tw[0]);
+    slot_col[0] = mk<R>(z[0].x + z[0].x, z[0].y + z[0].y);
+    const cx<R> z10 = mk<R>(z[10].x + z[10].x, z[10].y + z[10].y);
+    slot_col[10 * kSlotLd] = cmul(z10, t.get10());
 #pragma unroll
     for (int k1 = 1; k1 < 10; ++k1) {
-        const float2 p = z[k1], q = z[20 - k1];
-        const float2 ya = make_float2(p.x + q.x, p.y - q.y);
-        const float2 yb = make_float2(p.y + q.y, q.x - p.x);
-        slot_col[k1 * kSlotLd] = cmul(ya, t.tw[k1]);
-        slot_col[(10 + k1) * kSlotLd] = cmul(yb, t.tw[k1]);
+        const cx<R> p = z[k1], q = z[20 - k1];
+        const cx<R> ya = mk<R>(p.x + q.x, p.y - q.y);
+        const cx<R> yb = mk<R>(p.y + q.y, q.x - p.x);
+        const cx<R> w = t.get(k1);
+        slot_col[k1 * kSlotLd] = cmul(ya, w);
+        slot_col[(10 + k1) * kSlotLd] = cmul(yb, w);
     }
 }
 
 // ---- forward step 2: slot row c -> V[k2]
-SC_HD void fwd_step2(float2 (&v)[20], const float2* __restrict__ slot_row) {
+template <typename R>
+SC_HD void fwd_step2(cx<R> (&v)[20], const cx<R>* __restrict__ slot_row) {
 #pragma unroll
     for (int n2 = 0; n2 < 20; ++n2) v[n2] = slot_row[n2];
     dft20<false>(v);
@@ -81,66 +94,67 @@ SC_HD constexpr int own_bin(int k1, int k2) { return k2 < 10 ? k1 + 20 * k2 : (2
 
 // ---- |X|^2 of the bins owned by column thread c, written to the two frames' power rows
 //      (audio_lib.py:150-155: F = |stft|, P = F**2)
-SC_HD void store_power(const float2 (&v)[20], int c, float* __restrict__ pa, float* __restrict__ pb) {
+template <typename R>
+SC_HD void store_power(const cx<R> (&v)[20], int c, float* __restrict__ pa, float* __restrict__ pb) {
     if (c == 0) {
 #pragma unroll
         for (int k2 = 0; k2 <= 10; ++k2) {
-            const float2 p = v[k2], q = v[(20 - k2) % 20];
-            const float ar = p.x + q.x, ai = p.y - q.y, br = p.y + q.y, bi = q.x - p.x;
-            pa[20 * k2] = 0.25f * fmaf(ar, ar, ai * ai);
-            pb[20 * k2] = 0.25f * fmaf(br, br, bi * bi);
+            const cx<R> p = v[k2], q = v[(20 - k2) % 20];
+            const R ar = p.x + q.x, ai = p.y - q.y, br = p.y + q.y, bi = q.x - p.x;
+            pa[20 * k2] = (float)((R)0.25 * sc_fma(ar, ar, ai * ai));
+            pb[20 * k2] = (float)((R)0.25 * sc_fma(br, br, bi * bi));
         }
     } else if (c == 10) {
 #pragma unroll
         for (int k2 = 0; k2 < 10; ++k2) {
-            const float2 p = v[k2], q = v[19 - k2];
-            const float ar = p.x + q.x, ai = p.y - q.y, br = p.y + q.y, bi = q.x - p.x;
-            pa[10 + 20 * k2] = 0.25f * fmaf(ar, ar, ai * ai);
-            pb[10 + 20 * k2] = 0.25f * fmaf(br, br, bi * bi);
+            const cx<R> p = v[k2], q = v[19 - k2];
+            const R ar = p.x + q.x, ai = p.y - q.y, br = p.y + q.y, bi = q.x - p.x;
+            pa[10 + 20 * k2] = (float)((R)0.25 * sc_fma(ar, ar, ai * ai));
+            pb[10 + 20 * k2] = (float)((R)0.25 * sc_fma(br, br, bi * bi));
         }
     } else {
         const int k1 = c < 10 ? c : c - 10;
         float* __restrict__ row = c < 10 ? pa : pb;
 #pragma unroll
-        for (int k2 = 0; k2 < 10; ++k2) row[k1 + 20 * k2] = fmaf(v[k2].x, v[k2].x, v[k2].y * v[k2].y);
+        for (int k2 = 0; k2 < 10; ++k2) row[k1 + 20 * k2] = (float)sc_fma(v[k2].x, v[k2].x, v[k2].y * v[k2].y);
 #pragma unroll
         for (int k2 = 10; k2 < 20; ++k2)
-            row[(20 - k1) + 20 * (19 - k2)] = fmaf(v[k2].x, v[k2].x, v[k2].y * v[k2].y);
+            row[(20 - k1) + 20 * (19 - k2)] = (float)sc_fma(v[k2].x, v[k2].x, v[k2].y * v[k2].y);
     }
 }
 
 // unit-phase * amplitude (audio_lib.py:268-270: S = A * exp(1j*angle(X)); angle(0) = 0)
-SC_HD float2 impose(float2 x, float a) {
+SC_HD cxf impose(cxf x, float a) {
     const float n2 = fmaf(x.x, x.x, x.y * x.y);
     if (n2 > 0.0f) {
         const float s = a * sc_rsqrt(n2);
-        return make_float2(x.x * s, x.y * s);
+        return mk<float>(x.x * s, x.y * s);
     }
-    return make_float2(a, 0.0f);
+    return mk<float>(a, 0.0f);
 }
 
 // ---- Griffin-Lim phase update on the bins owned by column thread c, leaving v ready for the
 //      inverse step 2'.  amp_a / amp_b are the two frames' magnitude rows (201 floats each).
-SC_HD void gl_update(float2 (&v)[20], int c, const float* __restrict__ amp_a, const float* __restrict__ amp_b) {
+SC_HD void gl_update(cxf (&v)[20], int c, const float* __restrict__ amp_a, const float* __restrict__ amp_b) {
     if (c == 0) {
 #pragma unroll
         for (int k2 = 0; k2 <= 10; ++k2) {
             const int m = (20 - k2) % 20;
-            const float2 p = v[k2], q = v[m];
-            const float2 sa = impose(make_float2(p.x + q.x, p.y - q.y), amp_a[20 * k2]);
-            const float2 sb = impose(make_float2(p.y + q.y, q.x - p.x), amp_b[20 * k2]);
-            v[k2] = make_float2(sa.x - sb.y, sa.y + sb.x);
-            if (m != k2) v[m] = make_float2(sa.x + sb.y, sb.x - sa.y);
+            const cxf p = v[k2], q = v[m];
+            const cxf sa = impose(mk<float>(p.x + q.x, p.y - q.y), amp_a[20 * k2]);
+            const cxf sb = impose(mk<float>(p.y + q.y, q.x - p.x), amp_b[20 * k2]);
+            v[k2] = mk<float>(sa.x - sb.y, sa.y + sb.x);
+            if (m != k2) v[m] = mk<float>(sa.x + sb.y, sb.x - sa.y);
         }
     } else if (c == 10) {
 #pragma unroll
         for (int k2 = 0; k2 < 10; ++k2) {
             const int m = 19 - k2;
-            const float2 p = v[k2], q = v[m];
-            const float2 sa = impose(make_float2(p.x + q.x, p.y - q.y), amp_a[10 + 20 * k2]);
-            const float2 sb = impose(make_float2(p.y + q.y, q.x - p.x), amp_b[10 + 20 * k2]);
-            v[k2] = make_float2(sa.x - sb.y, sa.y + sb.x);
-            v[m] = make_float2(sa.x + sb.y, sb.x - sa.y);
+            const cxf p = v[k2], q = v[m];
+            const cxf sa = impose(mk<float>(p.x + q.x, p.y - q.y), amp_a[10 + 20 * k2]);
+            const cxf sb = impose(mk<float>(p.y + q.y, q.x - p.x), amp_b[10 + 20 * k2]);
+            v[k2] = mk<float>(sa.x - sb.y, sa.y + sb.x);
+            v[m] = mk<float>(sa.x + sb.y, sb.x - sa.y);
         }
     } else {
         const int k1 = c < 10 ? c : c - 10;
@@ -153,36 +167,36 @@ SC_HD void gl_update(float2 (&v)[20], int c, const float* __restrict__ amp_a, co
 // ---- Initial Griffin-Lim state S0 = A * exp(i*phase0) (audio_lib.py:255-256) laid out as the
 //      input of inverse step 2'.  The imaginary parts of bins 0 and 200 are dropped, as the
 //      reference's Hermitian extension + ".real" does inside librosa.istft.
-SC_HD float2 polar(float a, float ph) {
+SC_HD cxf polar(float a, float ph) {
     float s, c;
 #ifdef __CUDA_ARCH__
     sincosf(ph, &s, &c);
 #else
     s = sinf(ph); c = cosf(ph);
 #endif
-    return make_float2(a * c, a * s);
+    return mk<float>(a * c, a * s);
 }
 
-SC_HD void gl_init_state(float2 (&v)[20], int c, const float* __restrict__ amp_a, const float* __restrict__ amp_b,
+SC_HD void gl_init_state(cxf (&v)[20], int c, const float* __restrict__ amp_a, const float* __restrict__ amp_b,
                          const float* __restrict__ ph_a, const float* __restrict__ ph_b) {
     if (c == 0) {
 #pragma unroll
         for (int k2 = 0; k2 <= 10; ++k2) {
             const int m = (20 - k2) % 20;
-            float2 sa = polar(amp_a[20 * k2], ph_a[20 * k2]);
-            float2 sb = polar(amp_b[20 * k2], ph_b[20 * k2]);
+            cxf sa = polar(amp_a[20 * k2], ph_a[20 * k2]);
+            cxf sb = polar(amp_b[20 * k2], ph_b[20 * k2]);
             if (k2 == 0 || k2 == 10) { sa.y = 0.0f; sb.y = 0.0f; }
-            v[k2] = make_float2(sa.x - sb.y, sa.y + sb.x);
-            if (m != k2) v[m] = make_float2(sa.x + sb.y, sb.x - sa.y);
+            v[k2] = mk<float>(sa.x - sb.y, sa.y + sb.x);
+            if (m != k2) v[m] = mk<float>(sa.x + sb.y, sb.x - sa.y);
         }
     } else if (c == 10) {
 #pragma unroll
         for (int k2 = 0; k2 < 10; ++k2) {
             const int m = 19 - k2;
-            const float2 sa = polar(amp_a[10 + 20 * k2], ph_a[10 + 20 * k2]);
-            const float2 sb = polar(amp_b[10 + 20 * k2], ph_b[10 + 20 * k2]);
-            v[k2] = make_float2(sa.x - sb.y, sa.y + sb.x);
-            v[m] = make_float2(sa.x + sb.y, sb.x - sa.y);
+            const cxf sa = polar(amp_a[10 + 20 * k2], ph_a[10 + 20 * k2]);
+            const cxf sb = polar(amp_b[10 + 20 * k2], ph_b[10 + 20 * k2]);
+            v[k2] = mk<float>(sa.x - sb.y, sa.y + sb.x);
+            v[m] = mk<float>(sa.x + sb.y, sb.x - sa.y);
         }
     } else {
         const int k1 = c < 10 ? c : c - 10;
@@ -191,7 +205,7 @@ SC_HD void gl_init_state(float2 (&v)[20], int c, const float* __restrict__ amp_a
 #pragma unroll
         for (int k2 = 0; k2 < 20; ++k2) {
             const int b = own_bin(k1, k2);
-            float2 s = polar(amp[b], ph[b]);
+            cxf s = polar(amp[b], ph[b]);
             if (k2 >= 10) s.y = -s.y;
             v[k2] = s;
         }
@@ -199,7 +213,8 @@ SC_HD void gl_init_state(float2 (&v)[20], int c, const float* __restrict__ amp_a
 }
 
 // ---- inverse step 2': u[k2] = S[c-column] -> 20-point inverse DFT over k2 -> slot row c
-SC_HD void inv_step2(float2 (&u)[20], float2* __restrict__ slot_row) {
+template <typename R>
+SC_HD void inv_step2(cx<R> (&u)[20], cx<R>* __restrict__ slot_row) {
     dft20<true>(u);
 #pragma unroll
     for (int n2 = 0; n2 < 20; ++n2) slot_row[n2] = u[n2];
@@ -207,15 +222,17 @@ SC_HD void inv_step2(float2 (&u)[20], float2* __restrict__ slot_row) {
 
 // ---- inverse step 1': slot column j -> h[k1] -> 20-point inverse DFT over k1.
 //      On return h[n1] = 400 * (xA[20*n1 + j], xB[20*n1 + j]).
-SC_HD void inv_step1(float2 (&h)[20], const Twiddle& t, const float2* __restrict__ slot_col) {
+template <typename R, typename TW>
+SC_HD void inv_step1(cx<R> (&h)[20], const TW& t, const cx<R>* __restrict__ slot_col) {
     h[0] = slot_col[0];
-    h[10] = cmulc(slot_col[10 * kSlotLd], t.tw[0]);
+    h[10] = cmulc(slot_col[10 * kSlotLd], t.get10());
 #pragma unroll
     for (int k1 = 1; k1 < 10; ++k1) {
-        const float2 ha = cmulc(slot_col[k1 * kSlotLd], t.tw[k1]);
-        const float2 hb = cmulc(slot_col[(10 + k1) * kSlotLd], t.tw[k1]);
-        h[k1] = make_float2(ha.x - hb.y, ha.y + hb.x);
-        h[20 - k1] = make_float2(ha.x + hb.y, hb.x - ha.y);
+        const cx<R> w = t.get(k1);
+        const cx<R> ha = cmulc(slot_col[k1 * kSlotLd], w);
+        const cx<R> hb = cmulc(slot_col[(10 + k1) * kSlotLd], w);
+        h[k1] = mk<R>(ha.x - hb.y, ha.y + hb.x);
+        h[20 - k1] = mk<R>(ha.x + hb.y, hb.x - ha.y);
     }
     dft20<true>(h);
 }

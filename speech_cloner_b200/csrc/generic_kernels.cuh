@@ -12,20 +12,20 @@
 
 namespace scdsp {
 
-constexpr int kGenMaxNfft = 4096;
+constexpr int kGenMaxNfft = 2048;
 constexpr int kGenThreads = 256;
 constexpr int kGenFeFrames = 4;     // frames per front-end tile
 constexpr int kGenGlGroup = 2;      // frames transformed together in the Griffin-Lim kernel
 
 struct GenTables {
-    const float* win;       // analysis window, centre padded to n_fft
-    const float2* wn;       // exp(-2*pi*i*m/n_fft)
+    const double* win;      // analysis window, centre padded to n_fft (float64, like the reference's FFT input)
+    const cxd* wn;          // exp(-2*pi*i*m/n_fft) in float64
     int32_t n_fft, n_bins, hop;
 };
 
 struct GenGlTables {
     const float* win;       // hann, centre padded to n_fft
-    const float2* wn;
+    const cxf* wn;
     const double* win_sq;   // hann^2 (float64)
     const float* inv_wss;   // steady-state 1 / sum-square, period hop
     int32_t n_fft, n_bins, hop;
@@ -37,8 +37,8 @@ inline size_t gen_fe_smem_bytes(int n_fft, int hop, int n_mels) {
     (void)hop;
     const int bins = 1 + n_fft / 2;
     size_t s = 0;
-    s += gen_align(sizeof(float) * kGenFeFrames * n_fft);          // windowed frames
-    s += gen_align(sizeof(float2) * n_fft);                        // twiddles
+    s += gen_align(sizeof(double) * kGenFeFrames * n_fft);         // windowed frames
+    s += gen_align(sizeof(cxd) * n_fft);                           // twiddles
     s += gen_align(sizeof(float) * kGenFeFrames * bins);           // power
     s += gen_align(sizeof(float2) * bins);                         // mel weights
     s += gen_align(sizeof(int32_t) * (n_mels + 2));                // mel interval starts
@@ -48,18 +48,19 @@ inline size_t gen_fe_smem_bytes(int n_fft, int hop, int n_mels) {
 }
 
 // direct real DFT of `xw` (n_fft windowed samples) at bin k
-__device__ __forceinline__ float2 dft_bin(const float* __restrict__ xw, const float2* __restrict__ wn, int n_fft, int k) {
-    float re = 0.f, im = 0.f;
+template <typename R>
+__device__ __forceinline__ cx<R> dft_bin(const R* __restrict__ xw, const cx<R>* __restrict__ wn, int n_fft, int k) {
+    R re = 0, im = 0;
     int idx = 0;
     for (int n = 0; n < n_fft; ++n) {
-        const float2 w = wn[idx];
-        const float x = xw[n];
-        re = fmaf(x, w.x, re);
-        im = fmaf(x, w.y, im);
+        const cx<R> w = wn[idx];
+        const R x = xw[n];
+        re = sc_fma(x, w.x, re);
+        im = sc_fma(x, w.y, im);
         idx += k;
         if (idx >= n_fft) idx -= n_fft;
     }
-    return make_float2(re, im);
+    return mk<R>(re, im);
 }
 
 __global__ void __launch_bounds__(kGenThreads)
@@ -68,8 +69,8 @@ k_gen_fe_pass_a(const float* __restrict__ wav, Ragged rg, GenTables gt, FeTables
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n_fft = gt.n_fft, bins = gt.n_bins, hop = gt.hop, n_mels = tb.n_mels;
     unsigned char* sp = smem_raw;
-    float* xw = reinterpret_cast<float*>(sp);            sp += gen_align(sizeof(float) * kGenFeFrames * n_fft);
-    float2* wn = reinterpret_cast<float2*>(sp);          sp += gen_align(sizeof(float2) * n_fft);
+    double* xw = reinterpret_cast<double*>(sp);          sp += gen_align(sizeof(double) * kGenFeFrames * n_fft);
+    cxd* wn = reinterpret_cast<cxd*>(sp);                sp += gen_align(sizeof(cxd) * n_fft);
     float* power = reinterpret_cast<float*>(sp);         sp += gen_align(sizeof(float) * kGenFeFrames * bins);
     float2* mel_w = reinterpret_cast<float2*>(sp);       sp += gen_align(sizeof(float2) * bins);
     int32_t* istart = reinterpret_cast<int32_t*>(sp);    sp += gen_align(sizeof(int32_t) * (n_mels + 2));
@@ -92,7 +93,7 @@ k_gen_fe_pass_a(const float* __restrict__ wav, Ragged rg, GenTables gt, FeTables
         const int64_t r = reflect_idx((int64_t)(t0 + f) * hop + n - n_fft / 2, L);
         const float cur = gain * __ldg(y + r);
         const float prev = r > 0 ? gain * __ldg(y + r - 1) : 0.0f;
-        xw[e] = (float)((double)cur - c * (double)prev) * __ldg(gt.win + n);
+        xw[e] = ((double)cur - c * (double)prev) * __ldg(gt.win + n);
     }
     for (int i = tid; i < n_fft; i += kGenThreads) wn[i] = gt.wn[i];
     for (int i = tid; i < bins; i += kGenThreads) mel_w[i] = tb.mel_w[i];
@@ -100,8 +101,8 @@ k_gen_fe_pass_a(const float* __restrict__ wav, Ragged rg, GenTables gt, FeTables
     __syncthreads();
     for (int e = tid; e < nfr * bins; e += kGenThreads) {
         const int f = e / bins, k = e - f * bins;
-        const float2 x = dft_bin(xw + f * n_fft, wn, n_fft, k);
-        power[e] = fmaf(x.x, x.x, x.y * x.y);
+        const cxd x = dft_bin<double>(xw + f * n_fft, wn, n_fft, k);
+        power[e] = (float)fma(x.x, x.x, x.y * x.y);
     }
     __syncthreads();
     fe_epilogue_a<kGenThreads>(power, kGenFeFrames, bins, nfr, mel_w, istart, tb, mel_db, red, stat + u,
@@ -120,8 +121,8 @@ inline size_t gen_gl_smem_bytes(int n_fft, int hop) {
     const int bins = 1 + n_fft / 2;
     size_t s = 0;
     s += gen_align(sizeof(float) * kGenGlGroup * n_fft);                         // windowed frames / time output
-    s += gen_align(sizeof(float2) * kGenGlGroup * bins);                         // spectra
-    s += gen_align(sizeof(float2) * n_fft);                                      // twiddles
+    s += gen_align(sizeof(cxf) * kGenGlGroup * bins);                         // spectra
+    s += gen_align(sizeof(cxf) * n_fft);                                      // twiddles
     s += gen_align(sizeof(float) * n_fft);                                       // window
     s += gen_align(sizeof(float) * (gen_gl_out_per_tile(n_fft, hop)));           // accumulator
     return s;
@@ -148,8 +149,8 @@ k_gen_gl_iter(const GlJob* __restrict__ jobs, int n_jobs, const int32_t* __restr
     const int out_per_tile = gen_gl_out_per_tile(n_fft, hop);
     unsigned char* sp = smem_raw;
     float* xt = reinterpret_cast<float*>(sp);        sp += gen_align(sizeof(float) * kGenGlGroup * n_fft);
-    float2* spec = reinterpret_cast<float2*>(sp);    sp += gen_align(sizeof(float2) * kGenGlGroup * bins);
-    float2* wn = reinterpret_cast<float2*>(sp);      sp += gen_align(sizeof(float2) * n_fft);
+    cxf* spec = reinterpret_cast<cxf*>(sp);       sp += gen_align(sizeof(cxf) * kGenGlGroup * bins);
+    cxf* wn = reinterpret_cast<cxf*>(sp);         sp += gen_align(sizeof(cxf) * n_fft);
     float* win = reinterpret_cast<float*>(sp);       sp += gen_align(sizeof(float) * n_fft);
     float* acc = reinterpret_cast<float*>(sp);
 
@@ -187,14 +188,14 @@ k_gen_gl_iter(const GlJob* __restrict__ jobs, int n_jobs, const int32_t* __restr
         for (int e = tid; e < ng * bins; e += kGenThreads) {
             const int g = e / bins, k = e - g * bins;
             const int64_t f = fg + g;
-            float2 s = make_float2(0.f, 0.f);
+            cxf s = mk<float>(0.f, 0.f);
             if (f >= job.f_lo && f < (int64_t)job.f_lo + job.f_cnt) {
                 const int64_t row = job.amp_row0 + (f - job.f_lo);
                 const float a = __ldg(amp + row * bins + k);
                 if (init) {
                     s = polar(a, __ldg(phase0 + row * bins + k));
                 } else {
-                    s = impose(dft_bin(xt + g * n_fft, wn, n_fft, k), a);
+                    s = impose(dft_bin<float>(xt + g * n_fft, wn, n_fft, k), a);
                 }
                 if (k == 0 || k == bins - 1) s.y = 0.f;      // istft keeps only the real part there
             }
@@ -204,11 +205,11 @@ k_gen_gl_iter(const GlJob* __restrict__ jobs, int n_jobs, const int32_t* __restr
         // inverse real DFT, window; x[n] = (1/N) (S0 + (-1)^n S_{N/2} + 2 sum_k Re(S_k e^{+i 2 pi k n / N}))
         for (int e = tid; e < ng * n_fft; e += kGenThreads) {
             const int g = e / n_fft, n = e - g * n_fft;
-            const float2* __restrict__ s = spec + g * bins;
+            const cxf* __restrict__ s = spec + g * bins;
             float a = 0.f;
             int idx = n;
             for (int k = 1; k < bins - 1; ++k) {
-                const float2 w = wn[idx];
+                const cxf w = wn[idx];
                 a = fmaf(s[k].x, w.x, a);
                 a = fmaf(s[k].y, w.y, a);
                 idx += n;

@@ -33,11 +33,12 @@ struct GlJob {
 };
 
 struct GlTables {
-    const float2* w400;
+    const cxf* w400;
     const float* win_half;     // 0.5 * hann (forward), centre padded to 400
     const float* win_inv;      // hann / 400 (inverse)
     const double* win_sq;      // hann^2 in float64 (window_sumsquare terms)
     const float* inv_wss;      // steady-state 1 / sum-square, period = hop
+    const float* zero_row;     // 201 zeros: magnitude row of a frame that does not exist
 };
 
 // 1 / window_sumsquare at padded position p (librosa 0.6 filters.window_sumsquare, float32
@@ -56,7 +57,7 @@ struct GlSmem {
     float span[kGlSpan];
     float win_half[kNfft];
     float win_inv[kNfft];
-    float2 slots[kFeUnits * kUnitSlots];   // reused as seg[16][480] floats after the inverse
+    cxf slots[kFeUnits * kUnitSlots];   // reused as seg[16][480] floats after the inverse
 };
 
 template <bool INIT>
@@ -93,35 +94,40 @@ k_gl_iter(const GlJob* __restrict__ jobs, int n_jobs, const int32_t* __restrict_
     const int j = tid - unit * kUnitThreads;
     Twiddle tw;
     load_twiddles(tw, tb.w400, j);
-    float2* unit_slots = sm.slots + unit * kUnitSlots;
+    cxf* unit_slots = sm.slots + unit * kUnitSlots;
     __syncthreads();
 
+    // Frames of this unit.  A frame that does not exist (outside [0, T) or outside the rows this job
+    // holds) is fed exact zeros end to end: the two frames of a pair share one packed transform, so
+    // any garbage in the partner would change the rounding of the real frame and break the
+    // bit-identity of time-chunked runs.
+    const int64_t fa = t0 + 2 * unit, fb = fa + 1;
+    const bool va = fa >= job.f_lo && fa < (int64_t)job.f_lo + job.f_cnt && fa < T;
+    const bool vb = fb >= job.f_lo && fb < (int64_t)job.f_lo + job.f_cnt && fb < T;
+    const float ka = va ? 1.0f : 0.0f, kb = vb ? 1.0f : 0.0f;
     if (!INIT) {
         float s[24];
         const float* __restrict__ src = sm.span + unit * (2 * kHop) + j;
 #pragma unroll
         for (int m = 0; m < 24; ++m) s[m] = src[20 * m];
-        float2 z[20];
+        cxf z[20];
 #pragma unroll
         for (int n1 = 0; n1 < 20; ++n1) {
             const float w = sm.win_half[20 * n1 + j];
-            z[n1] = make_float2(s[n1] * w, s[n1 + 4] * w);
+            z[n1] = mk<float>(s[n1] * (w * ka), s[n1 + 4] * (w * kb));
         }
         fwd_step1(z, tw, unit_slots + j);
         __syncthreads();
     }
-    // frames of this unit and their magnitude rows
-    const int64_t fa = t0 + 2 * unit, fb = fa + 1;
-    const bool va = fa >= job.f_lo && fa < (int64_t)job.f_lo + job.f_cnt && fa < T;
-    const bool vb = fb >= job.f_lo && fb < (int64_t)job.f_lo + job.f_cnt && fb < T;
     {
         const int64_t ra = job.amp_row0 + (va ? fa - job.f_lo : 0);
         const int64_t rb = job.amp_row0 + (vb ? fb - job.f_lo : 0);
-        const float* __restrict__ amp_a = amp + ra * kBins;
-        const float* __restrict__ amp_b = amp + rb * kBins;
-        float2 v[20];
+        const float* __restrict__ amp_a = va ? amp + ra * kBins : tb.zero_row;
+        const float* __restrict__ amp_b = vb ? amp + rb * kBins : tb.zero_row;
+        cxf v[20];
         if (INIT) {
-            gl_init_state(v, j, amp_a, amp_b, phase0 + ra * kBins, phase0 + rb * kBins);
+            gl_init_state(v, j, amp_a, amp_b, va ? phase0 + ra * kBins : tb.zero_row,
+                          vb ? phase0 + rb * kBins : tb.zero_row);
         } else {
             fwd_step2(v, unit_slots + j * kSlotLd);
             gl_update(v, j, amp_a, amp_b);
@@ -131,14 +137,13 @@ k_gl_iter(const GlJob* __restrict__ jobs, int n_jobs, const int32_t* __restrict_
     __syncthreads();
     float comb[24];
     {
-        float2 h[20];
+        cxf h[20];
         inv_step1(h, tw, unit_slots + j);
-        const float ka = va ? 1.0f : 0.0f, kb = vb ? 1.0f : 0.0f;
 #pragma unroll
         for (int m = 0; m < 24; ++m) {
             float a = 0.f;
-            if (m < 20) a = h[m].x * (sm.win_inv[20 * m + j] * ka);
-            if (m >= 4) a += h[m - 4].y * (sm.win_inv[20 * (m - 4) + j] * kb);
+            if (m < 20) a = h[m].x * sm.win_inv[20 * m + j];
+            if (m >= 4) a += h[m - 4].y * sm.win_inv[20 * (m - 4) + j];
             comb[m] = a;
         }
     }

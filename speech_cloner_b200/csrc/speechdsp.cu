@@ -88,22 +88,27 @@ struct sc_plan {
     int device = 0;
     // constant tables (one allocation)
     DevBuf tables;
-    const float2* w400 = nullptr;
+    const cxf* w400 = nullptr;
+    const cxd* w400_d = nullptr;
+    const double* fe_win_half_d = nullptr;
     const float* fe_win_half = nullptr;
     const float* gl_win_half = nullptr;
     const float* gl_win_inv = nullptr;
     const double* gl_win_sq = nullptr;
     const float* gl_inv_wss = nullptr;
+    const float* zero_row = nullptr;
     const float2* mel_w = nullptr;
     const int32_t* mel_istart = nullptr;
     const int32_t* mel_chunk = nullptr;
     const float* dct_t = nullptr;
     int n_mfcc_pad = 0;
     // generic-size tables
-    const float* g_fe_win = nullptr;     // analysis window (n_fft)
+    const double* g_fe_win = nullptr;    // analysis window (n_fft), float64
     const float* g_gl_win = nullptr;     // hann (n_fft)
-    const float2* g_wn = nullptr;        // exp(-2*pi*i*m/n_fft)
+    const cxf* g_wn = nullptr;           // exp(-2*pi*i*m/n_fft)
+    const cxd* g_wn_d = nullptr;
     const double* g_win_sq = nullptr;
+    bool fp32_fft = false;               // sc_params.fft_precision == 1
     // host copies used by generic paths / tests
     std::vector<double> fe_window, gl_window;
     // per-call workspaces
@@ -227,12 +232,13 @@ extern "C" int sc_plan_create(const sc_params* p, sc_plan** out) {
     if (!p || !out) return fail(SC_ERR_INVALID, "sc_plan_create: null argument");
     *out = nullptr;
     if (p->n_fft < 2 || (p->n_fft & 1)) return fail(SC_ERR_INVALID, "n_fft must be even and >= 2");
-    if (p->n_fft > kGenMaxNfft) return fail(SC_ERR_UNSUPPORTED, "n_fft larger than 8192 is not supported");
+    if (p->n_fft > kGenMaxNfft) return fail(SC_ERR_UNSUPPORTED, "n_fft larger than 2048 is not supported");
     if (p->win_length < 1 || p->win_length > p->n_fft) return fail(SC_ERR_INVALID, "win_length must be in [1, n_fft]");
     if (p->hop_length < 1) return fail(SC_ERR_INVALID, "hop_length must be >= 1");
     if (p->n_mels < 1 || p->n_mels > kMaxMels) return fail(SC_ERR_INVALID, "n_mels must be in [1, 128]");
     if (p->n_mfcc < 1 || p->n_mfcc > p->n_mels) return fail(SC_ERR_INVALID, "n_mfcc must be in [1, n_mels]");
     if (p->sample_rate < 1) return fail(SC_ERR_INVALID, "sample_rate must be positive");
+    if (p->fft_precision != 0 && p->fft_precision != 1) return fail(SC_ERR_INVALID, "fft_precision must be 0 (float64) or 1 (float32)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -243,6 +249,7 @@ extern "C" int sc_plan_create(const sc_params* p, sc_plan** out) {
     pl->prm.window_host = nullptr;
     pl->n_bins = 1 + p->n_fft / 2;
     pl->fast = (p->n_fft == kNfft && p->hop_length == kHop);
+    pl->fp32_fft = p->fft_precision == 1;
     cudaGetDevice(&pl->device);
 
     std::vector<double> w = p->window_host ? std::vector<double>(p->window_host, p->window_host + p->win_length)
@@ -252,19 +259,21 @@ extern "C" int sc_plan_create(const sc_params* p, sc_plan** out) {
 
     const int n_fft = p->n_fft;
     Blob b;
-    std::vector<float2> wn(n_fft);
+    std::vector<cxf> wn(n_fft);
+    std::vector<cxd> wn_d(n_fft);
     for (int m = 0; m < n_fft; ++m) {
         const double a = -2.0 * M_PI * m / n_fft;
-        wn[m] = make_float2((float)cos(a), (float)sin(a));
+        wn_d[m] = mk<double>(cos(a), sin(a));
+        wn[m] = mk<float>((float)wn_d[m].x, (float)wn_d[m].y);
     }
-    std::vector<float> fe_half(n_fft), gl_half(n_fft), gl_inv(n_fft), fe_w(n_fft), gl_w(n_fft);
-    std::vector<double> gl_sq(n_fft);
+    std::vector<float> fe_half(n_fft), gl_half(n_fft), gl_inv(n_fft), gl_w(n_fft);
+    std::vector<double> gl_sq(n_fft), fe_half_d(n_fft);
     for (int i = 0; i < n_fft; ++i) {
         fe_half[i] = (float)(0.5 * pl->fe_window[i]);
         gl_half[i] = (float)(0.5 * pl->gl_window[i]);
         gl_inv[i] = (float)(pl->gl_window[i] / n_fft);
         gl_sq[i] = pl->gl_window[i] * pl->gl_window[i];
-        fe_w[i] = (float)pl->fe_window[i];
+        fe_half_d[i] = 0.5 * pl->fe_window[i];
         gl_w[i] = (float)pl->gl_window[i];
     }
     std::vector<float> inv_wss = build_inv_wss(pl->gl_window, n_fft, p->hop_length);
@@ -280,7 +289,10 @@ extern "C" int sc_plan_create(const sc_params* p, sc_plan** out) {
         }
     const size_t o_wn = b.add(wn), o_feh = b.add(fe_half), o_glh = b.add(gl_half), o_gli = b.add(gl_inv);
     const size_t o_sq = b.add(gl_sq), o_wss = b.add(inv_wss), o_mw = b.add(ms.w), o_mi = b.add(ms.istart);
-    const size_t o_mc = b.add(ms.chunk), o_dct = b.add(dct), o_few = b.add(fe_w), o_glw = b.add(gl_w);
+    const size_t o_mc = b.add(ms.chunk), o_dct = b.add(dct), o_few = b.add(pl->fe_window), o_glw = b.add(gl_w);
+    const size_t o_wnd = b.add(wn_d), o_fehd = b.add(fe_half_d);
+    std::vector<float> zeros(pl->n_bins, 0.f);
+    const size_t o_zero = b.add(zeros);
     if (pl->tables.ensure(b.bytes.size())) { delete pl; return SC_ERR_CUDA; }
     e = cudaMemcpy(pl->tables.p, b.bytes.data(), b.bytes.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
@@ -289,17 +301,20 @@ extern "C" int sc_plan_create(const sc_params* p, sc_plan** out) {
         return fail(SC_ERR_CUDA, std::string("plan upload: ") + cudaGetErrorString(e));
     }
     const unsigned char* base = static_cast<const unsigned char*>(pl->tables.p);
-    pl->w400 = (const float2*)(base + o_wn);       pl->g_wn = pl->w400;
+    pl->w400 = (const cxf*)(base + o_wn);          pl->g_wn = pl->w400;
+    pl->w400_d = (const cxd*)(base + o_wnd);       pl->g_wn_d = pl->w400_d;
+    pl->fe_win_half_d = (const double*)(base + o_fehd);
     pl->fe_win_half = (const float*)(base + o_feh);
     pl->gl_win_half = (const float*)(base + o_glh);
     pl->gl_win_inv = (const float*)(base + o_gli);
     pl->gl_win_sq = (const double*)(base + o_sq);  pl->g_win_sq = pl->gl_win_sq;
     pl->gl_inv_wss = (const float*)(base + o_wss);
+    pl->zero_row = (const float*)(base + o_zero);
     pl->mel_w = (const float2*)(base + o_mw);
     pl->mel_istart = (const int32_t*)(base + o_mi);
     pl->mel_chunk = (const int32_t*)(base + o_mc);
     pl->dct_t = (const float*)(base + o_dct);
-    pl->g_fe_win = (const float*)(base + o_few);
+    pl->g_fe_win = (const double*)(base + o_few);
     pl->g_gl_win = (const float*)(base + o_glw);
     *out = pl;
     return SC_OK;
@@ -318,7 +333,8 @@ extern "C" int64_t sc_num_frames(const sc_plan* pl, int64_t n) { return pl ? 1 +
 
 static FeTables fe_tables(const sc_plan* pl) {
     FeTables t;
-    t.w400 = pl->w400; t.win_half = pl->fe_win_half; t.mel_w = pl->mel_w; t.mel_istart = pl->mel_istart;
+    t.w400 = pl->w400; t.win_half = pl->fe_win_half; t.w400_d = pl->w400_d; t.win_half_d = pl->fe_win_half_d;
+    t.mel_w = pl->mel_w; t.mel_istart = pl->mel_istart;
     t.mel_chunk = pl->mel_chunk; t.dct_t = pl->dct_t;
     t.n_mels = pl->prm.n_mels; t.n_mfcc = pl->prm.n_mfcc; t.n_mfcc_pad = pl->n_mfcc_pad;
     return t;
@@ -349,6 +365,7 @@ extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* s
     const int hop = pl->prm.hop_length;
     std::vector<int64_t> slen(n), so(soff, soff + n), fo(foff, foff + n);
     std::vector<int32_t> fcnt(n), pre_abs(n + 1), pre_a(n + 1), pre_b(n + 1);
+    std::vector<int64_t> heap_off(n + 1);
     int64_t total_frames_span = 0;
     const int a_frames = pl->fast ? kFeFrames : kGenFeFrames;
     for (int u = 0; u < n; ++u) {
@@ -362,8 +379,10 @@ extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* s
         if (fo[u] + T > total_frames_span) total_frames_span = fo[u] + T;
     }
     pre_abs[0] = pre_a[0] = pre_b[0] = 0;
+    heap_off[0] = 0;
     for (int u = 0; u < n; ++u) {
-        const int64_t ta = pre_abs[u] + (slen[u] + kAbsChunk - 1) / kAbsChunk;
+        const int64_t ta = pre_abs[u] + (int64_t(1) << abs_depth(slen[u]));
+        heap_off[u + 1] = heap_off[u] + (int64_t(2) << abs_depth(slen[u]));
         const int64_t tb = pre_a[u] + (fcnt[u] + a_frames - 1) / a_frames;
         const int64_t tc = pre_b[u] + (fcnt[u] + kFbFrames - 1) / kFbFrames;
         if (ta > INT32_MAX || tb > INT32_MAX) return fail(SC_ERR_INVALID, "sc_frontend_batch: batch too large");
@@ -371,18 +390,18 @@ extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* s
     }
     Blob b;
     const size_t o_so = b.add(so), o_sl = b.add(slen), o_fo = b.add(fo), o_fc = b.add(fcnt);
-    const size_t o_pabs = b.add(pre_abs), o_pa = b.add(pre_a), o_pb = b.add(pre_b);
+    const size_t o_pabs = b.add(pre_abs), o_pa = b.add(pre_a), o_pb = b.add(pre_b), o_heap = b.add(heap_off);
     if (int rc = upload_blob(pl, b, st)) return rc;
 
     // workspace: stats | abs partials | raw mel
     const size_t w_stat = 0;
     const size_t w_part = (sizeof(UttStat) * n + 255) & ~size_t(255);
-    const size_t w_mel = (w_part + sizeof(double) * pre_abs[n] + 255) & ~size_t(255);
+    const size_t w_mel = (w_part + sizeof(float) * (size_t)heap_off[n] + 255) & ~size_t(255);
     const size_t w_end = w_mel + sizeof(float) * (size_t)total_frames_span * pl->prm.n_mels;
     if (int rc = pl->work.ensure(w_end)) return rc;
     unsigned char* wb = static_cast<unsigned char*>(pl->work.p);
     UttStat* stat = reinterpret_cast<UttStat*>(wb + w_stat);
-    double* partial = reinterpret_cast<double*>(wb + w_part);
+    float* heap = reinterpret_cast<float*>(wb + w_part);
     float* mel_raw = reinterpret_cast<float*>(wb + w_mel);
 
     Ragged rg;
@@ -394,25 +413,29 @@ extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* s
 
     if (fp.use_gain) {
         rg.tile_prefix = at<int32_t>(pl, o_pabs);
-        k_abs_partial<<<pre_abs[n], 256, 0, st>>>(wav, rg, partial);
+        k_abs_pairwise<<<pre_abs[n], kAbsThreads, 0, st>>>(wav, rg, at<int64_t>(pl, o_heap), heap);
         SC_LAUNCHED();
     }
     rg.tile_prefix = at<int32_t>(pl, o_pabs);
-    k_gain_finalize<<<(n + 3) / 4, 128, 0, st>>>(rg, partial, stat, fp.mean_abs_amp_norm, fp.use_gain);
+    k_gain_finalize<<<(n + 3) / 4, 128, 0, st>>>(rg, at<int64_t>(pl, o_heap), heap, stat, fp.mean_abs_amp_norm, fp.use_gain, nullptr);
     SC_LAUNCHED();
 
     rg.tile_prefix = at<int32_t>(pl, o_pa);
     if (pl->fast) {
-        const size_t smem = sizeof(FeSmemA) + sizeof(float) * kFeFrames * (pl->prm.n_mels + 1);
         static bool attr_set = false;
         if (!attr_set) {
-            SC_CUDA(cudaFuncSetAttribute(k_fe_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+            SC_CUDA(cudaFuncSetAttribute(k_fe_pass_a<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+            SC_CUDA(cudaFuncSetAttribute(k_fe_pass_a<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             attr_set = true;
         }
-        k_fe_pass_a<<<pre_a[n], kFeThreads, smem, st>>>(wav, rg, tb, fp, stat, pdb, mel_raw);
+        const size_t mel_bytes = sizeof(float) * kFeFrames * (pl->prm.n_mels + 1);
+        if (pl->fp32_fft)
+            k_fe_pass_a<float><<<pre_a[n], kFeThreads, sizeof(FeSmemA<float>) + mel_bytes, st>>>(wav, rg, tb, fp, stat, pdb, mel_raw);
+        else
+            k_fe_pass_a<double><<<pre_a[n], kFeThreads, sizeof(FeSmemA<double>) + mel_bytes, st>>>(wav, rg, tb, fp, stat, pdb, mel_raw);
         SC_LAUNCHED();
     } else {
-        GenTables gt{pl->g_fe_win, pl->g_wn, pl->prm.n_fft, pl->n_bins, pl->prm.hop_length};
+        GenTables gt{pl->g_fe_win, pl->g_wn_d, pl->prm.n_fft, pl->n_bins, pl->prm.hop_length};
         const size_t smem = gen_fe_smem_bytes(pl->prm.n_fft, pl->prm.hop_length, pl->prm.n_mels);
         SC_CUDA(cudaFuncSetAttribute(k_gen_fe_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_gen_fe_pass_a<<<pre_a[n], kGenThreads, smem, st>>>(wav, rg, gt, tb, fp, stat, pdb, mel_raw);
@@ -427,6 +450,41 @@ extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* s
         k_fe_pass_b<<<pre_b[n], kFbThreads, smem, st>>>(rg, tb, fp, stat, mel_raw, pdb, mel, mfcc, pl->n_bins);
         SC_LAUNCHED();
     }
+    return SC_OK;
+}
+
+// np.abs(y).mean() per utterance, bit-identical to NumPy's float32 pairwise summation (:126)
+extern "C" int sc_mean_abs_batch(sc_plan* pl, const float* wav, const int64_t* soff, const int64_t* slen_in, int32_t n,
+                                 float* mean_out, void* stream) {
+    if (!pl || !wav || !soff || !mean_out) return fail(SC_ERR_INVALID, "sc_mean_abs_batch: null argument");
+    if (n <= 0) return SC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<int64_t> so(soff, soff + n), slen(n), heap_off(n + 1), fo(n, 0);
+    std::vector<int32_t> pre(n + 1), fc(n, 0);
+    pre[0] = 0; heap_off[0] = 0;
+    for (int u = 0; u < n; ++u) {
+        slen[u] = slen_in ? slen_in[u] : soff[u + 1] - soff[u];
+        if (slen[u] < 1) return fail(SC_ERR_INVALID, "sc_mean_abs_batch: empty utterance");
+        const int64_t t = pre[u] + (int64_t(1) << abs_depth(slen[u]));
+        if (t > INT32_MAX) return fail(SC_ERR_INVALID, "sc_mean_abs_batch: batch too large");
+        pre[u + 1] = (int32_t)t;
+        heap_off[u + 1] = heap_off[u] + (int64_t(2) << abs_depth(slen[u]));
+    }
+    Blob b;
+    const size_t o_so = b.add(so), o_sl = b.add(slen), o_fo = b.add(fo), o_fc = b.add(fc), o_p = b.add(pre), o_h = b.add(heap_off);
+    if (int rc = upload_blob(pl, b, st)) return rc;
+    const size_t w_heap = (sizeof(UttStat) * n + 255) & ~size_t(255);
+    if (int rc = pl->work.ensure(w_heap + sizeof(float) * (size_t)heap_off[n])) return rc;
+    unsigned char* wb = static_cast<unsigned char*>(pl->work.p);
+    Ragged rg;
+    rg.sample_off = at<int64_t>(pl, o_so); rg.sample_len = at<int64_t>(pl, o_sl);
+    rg.frame_off = at<int64_t>(pl, o_fo); rg.frame_cnt = at<int32_t>(pl, o_fc);
+    rg.tile_prefix = at<int32_t>(pl, o_p); rg.n_utts = n;
+    float* heap = reinterpret_cast<float*>(wb + w_heap);
+    k_abs_pairwise<<<pre[n], kAbsThreads, 0, st>>>(wav, rg, at<int64_t>(pl, o_h), heap);
+    SC_LAUNCHED();
+    k_gain_finalize<<<(n + 3) / 4, 128, 0, st>>>(rg, at<int64_t>(pl, o_h), heap, reinterpret_cast<UttStat*>(wb), 1.0, 1, mean_out);
+    SC_LAUNCHED();
     return SC_OK;
 }
 
@@ -543,7 +601,7 @@ extern "C" int sc_power_to_amp_batch(sc_plan* pl, const float* p, const int64_t*
 static GlTables gl_tables(const sc_plan* pl) {
     GlTables t;
     t.w400 = pl->w400; t.win_half = pl->gl_win_half; t.win_inv = pl->gl_win_inv;
-    t.win_sq = pl->gl_win_sq; t.inv_wss = pl->gl_inv_wss;
+    t.win_sq = pl->gl_win_sq; t.inv_wss = pl->gl_inv_wss; t.zero_row = pl->zero_row;
     return t;
 }
 

@@ -18,13 +18,14 @@ static void naive_rdft(const std::vector<double>& x, std::vector<double>& re, st
         }
 }
 
-int main() {
-    std::vector<float2> w400(kNfft);
+template <typename R>
+static int check(const char* name, double tol_pow, double tol_rt) {
+    std::vector<cx<R>> w400(kNfft);
     for (int m = 0; m < kNfft; ++m) {
         const double a = -2.0 * M_PI * m / kNfft;
-        w400[m] = make_float2((float)cos(a), (float)sin(a));
+        w400[m] = mk<R>((R)cos(a), (R)sin(a));
     }
-    srand(7);
+    srand(7);  // same data for both precisions
     std::vector<double> xa(kNfft), xb(kNfft);
     for (int n = 0; n < kNfft; ++n) {
         xa[n] = (rand() / (double)RAND_MAX - 0.5) * (0.5 - 0.5 * cos(2 * M_PI * n / kNfft));
@@ -33,18 +34,19 @@ int main() {
     std::vector<double> ar, ai, br, bi;
     naive_rdft(xa, ar, ai); naive_rdft(xb, br, bi);
 
-    std::vector<float2> slots(kUnitSlots);
-    Twiddle tw[20];
-    for (int j = 0; j < 20; ++j) load_twiddles(tw[j], w400.data(), j);
+    std::vector<cx<R>> slots(kUnitSlots);
+    TwReg<R> tw[20];
+    TwTab<R> twt[20];
+    for (int j = 0; j < 20; ++j) { tw[j].load(w400.data(), j); twt[j].load(w400.data(), j); }
 
     // ---------------- forward + power
     for (int j = 0; j < 20; ++j) {
-        float2 z[20];
-        for (int n1 = 0; n1 < 20; ++n1) z[n1] = make_float2(0.5f * (float)xa[20 * n1 + j], 0.5f * (float)xb[20 * n1 + j]);
-        fwd_step1(z, tw[j], &slots[j]);
+        cx<R> z[20];
+        for (int n1 = 0; n1 < 20; ++n1) z[n1] = mk<R>((R)(0.5 * xa[20 * n1 + j]), (R)(0.5 * xb[20 * n1 + j]));
+        if (j & 1) fwd_step1(z, tw[j], &slots[j]); else fwd_step1(z, twt[j], &slots[j]);   // both twiddle sources
     }
     std::vector<float> pa(kBins, -1.f), pb(kBins, -1.f);
-    float2 V[20][20];
+    cx<R> V[20][20];
     for (int c = 0; c < 20; ++c) {
         fwd_step2(V[c], &slots[c * kSlotLd]);
         store_power(V[c], c, pa.data(), pb.data());
@@ -55,8 +57,8 @@ int main() {
         pmax = fmax(pmax, fmax(ta, tb));
         perr = fmax(perr, fmax(fabs(pa[k] - ta), fabs(pb[k] - tb)));
     }
-    printf("power max %.4g  max abs err %.3g  rel %.3g\n", pmax, perr, perr / pmax);
-    int fail = perr / pmax > 2e-6;
+    printf("[%s] power max %.4g  max abs err %.3g  rel %.3g\n", name, pmax, perr, perr / pmax);
+    int fail = perr / pmax > tol_pow;
 
     // ---------------- forward -> gl_update with A = |X| (identity) -> inverse == input
     std::vector<float> ampa(kBins), ampb(kBins), pha(kBins), phb(kBins);
@@ -64,30 +66,42 @@ int main() {
         ampa[k] = (float)hypot(ar[k], ai[k]); ampb[k] = (float)hypot(br[k], bi[k]);
         pha[k] = (float)atan2(ai[k], ar[k]); phb[k] = (float)atan2(bi[k], br[k]);
     }
-    for (int mode = 0; mode < 2; ++mode) {
+    for (int mode = 0; mode < 3; ++mode) {
         for (int c = 0; c < 20; ++c) {
-            float2 u[20];
-            if (mode == 0) {
+            cx<R> u[20];
+            if (mode == 2) {                       // plain forward -> inverse, any precision
                 for (int i = 0; i < 20; ++i) u[i] = V[c][i];
-                gl_update(u, c, ampa.data(), ampb.data());
             } else {
-                gl_init_state(u, c, ampa.data(), ampb.data(), pha.data(), phb.data());
+                cxf uf[20];
+                if (mode == 0) {
+                    for (int i = 0; i < 20; ++i) uf[i] = mk<float>((float)V[c][i].x, (float)V[c][i].y);
+                    gl_update(uf, c, ampa.data(), ampb.data());
+                } else {
+                    gl_init_state(uf, c, ampa.data(), ampb.data(), pha.data(), phb.data());
+                }
+                for (int i = 0; i < 20; ++i) u[i] = mk<R>((R)uf[i].x, (R)uf[i].y);
             }
             inv_step2(u, &slots[c * kSlotLd]);
         }
         double rerr = 0, xmax = 0;
         for (int j = 0; j < 20; ++j) {
-            float2 h[20];
-            inv_step1(h, tw[j], &slots[j]);
+            cx<R> h[20];
+            if (j & 1) inv_step1(h, twt[j], &slots[j]); else inv_step1(h, tw[j], &slots[j]);
             for (int n1 = 0; n1 < 20; ++n1) {
                 rerr = fmax(rerr, fabs(h[n1].x / 400.0 - xa[20 * n1 + j]));
                 rerr = fmax(rerr, fabs(h[n1].y / 400.0 - xb[20 * n1 + j]));
                 xmax = fmax(xmax, fmax(fabs(xa[20 * n1 + j]), fabs(xb[20 * n1 + j])));
             }
         }
-        printf("mode %d roundtrip max abs err %.3g (signal max %.3g)\n", mode, rerr, xmax);
-        fail |= rerr / xmax > 5e-6;
+        printf("[%s] mode %d roundtrip max abs err %.3g (signal max %.3g)\n", name, mode, rerr, xmax);
+        fail |= rerr / xmax > (mode == 2 ? tol_rt : 5e-6);
     }
+    return fail;
+}
+
+int main() {
+    int fail = check<float>("float32", 2e-6, 5e-6);
+    fail |= check<double>("float64", 1e-7, 1e-14);   // power is stored as float32
     printf(fail ? "FAIL\n" : "OK\n");
     return fail;
 }
