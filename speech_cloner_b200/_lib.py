@@ -56,6 +56,8 @@ PROTOTYPES = {
     "sc_transpose_to_f32": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
     "sc_griffinlim_chunk_step": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64,
                                            C.c_int64, _P, C.c_int64, C.c_int64, _P]),
+    "sc_profile_enable": (C.c_int, [_P, C.c_int32]),
+    "sc_profile_read": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "sc_launch_count": (C.c_int64, []),
     "sc_launch_count_reset": (None, []),
     "sc_last_error": (C.c_char_p, []),

@@ -117,6 +117,15 @@ class DspPlan:
     def num_frames(self, n_samples: int) -> int:
         return 1 + int(n_samples) // self.hop_length
 
+    def profile(self, on: bool) -> None:
+        """Record CUDA events between the kernels of the next batch call (see ``sc_profile_enable``)."""
+        _lib.check(self._lib.sc_profile_enable(self._h, int(bool(on))), "sc_profile_enable")
+
+    def profile_read(self):
+        out = (C.c_double * 4)()
+        _lib.check(self._lib.sc_profile_read(self._h, out), "sc_profile_read")
+        return [float(v) for v in out]
+
 
 def _window_array(window, win_length: int) -> np.ndarray:
     """librosa 0.6 ``filters.get_window(window, win_length, fftbins=True)`` (audio_lib.py:145)."""
@@ -523,3 +532,76 @@ def launch_count() -> int:
 
 def launch_count_reset() -> None:
     _lib.load().sc_launch_count_reset()
+
+
+# ------------------------------------------------------------------ host-buffer pipeline
+class FrontendPipeline:
+    """Featurise a fixed ragged layout from HOST buffers: pinned H2D -> kernels -> pinned D2H.
+
+    This is the dataset-builder path (the readers' per-utterance loop, TIMIT_reader.py:169-201, as
+    one call): the batch is cut into ``n_chunks`` utterance groups that rotate over ``n_streams``
+    CUDA streams, so the upload of chunk c+1 and the download of chunk c-1 overlap the kernels of
+    chunk c.  Each stream owns its own plan (workspace).  Results land in three packed pinned host
+    arrays; ``views()`` gives the per-utterance (MFCC, M_dB, P_dB) triples.
+    """
+
+    def __init__(self, lengths: Sequence[int], n_chunks: int = 8, n_streams: int = 3, **plan_kw):
+        torch = _require_cuda()
+        self.torch = torch
+        self.plans = [DspPlan(**plan_kw) for _ in range(n_streams)]
+        p0 = self.plans[0]
+        self.layout = FrontendLayout(lengths, p0.hop_length)
+        lay = self.layout
+        n = len(lay.lengths)
+        n_chunks = max(1, min(n_chunks, n))
+        # contiguous utterance groups with ~equal frame counts
+        bounds, acc, target = [0], 0, lay.total_frames / n_chunks
+        for i, t in enumerate(lay.frames):
+            acc += _align(t, 4)
+            if acc >= target * len(bounds) and len(bounds) < n_chunks and i + 1 < n:
+                bounds.append(i + 1)
+        bounds.append(n)
+        self.chunks = []
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            sub = FrontendLayout(lay.lengths[a:b], p0.hop_length)
+            self.chunks.append((a, b, sub, lay.sample_offsets[a], lay.frame_offsets[a]))
+        self.streams = [torch.cuda.Stream() for _ in range(n_streams)]
+        self.wav_host = torch.zeros(lay.total_samples, dtype=torch.float32).pin_memory()
+        self.wav_dev = torch.empty(lay.total_samples, dtype=torch.float32, device="cuda")
+        shapes = ((lay.total_frames, p0.mfcc_width), (lay.total_frames, p0.n_mels), (lay.total_frames, p0.n_bins))
+        self.out_dev = tuple(torch.empty(s, dtype=torch.float32, device="cuda") for s in shapes)
+        self.out_host = tuple(torch.empty(s, dtype=torch.float32).pin_memory() for s in shapes)
+        self.h2d_bytes = sum(c[2].total_samples for c in self.chunks) * 4
+        self.d2h_bytes = sum(c[2].total_frames for c in self.chunks) * 4 * (p0.mfcc_width + p0.n_mels + p0.n_bins)
+
+    def load(self, wavs) -> None:
+        """Pack host waveforms into the pinned staging buffer (not part of ``run``)."""
+        hv = self.wav_host.numpy()
+        for w, o in zip(wavs, self.layout.sample_offsets):
+            hv[o:o + len(w)] = w
+
+    def run(self):
+        """One pass: H2D, kernels, D2H for every chunk; returns after the last byte is on the host."""
+        torch = self.torch
+        cur = torch.cuda.current_stream()
+        for s in self.streams:
+            s.wait_stream(cur)
+        for i, (a, b, sub, s_off, f_off) in enumerate(self.chunks):
+            st = self.streams[i % len(self.streams)]
+            plan = self.plans[i % len(self.plans)]
+            with torch.cuda.stream(st):
+                ns, nf = sub.total_samples, sub.total_frames
+                self.wav_dev[s_off:s_off + ns].copy_(self.wav_host[s_off:s_off + ns], non_blocking=True)
+                outs = tuple(o[f_off:f_off + nf] for o in self.out_dev)
+                frontend_device(plan, self.wav_dev[s_off:s_off + ns], sub, outs)
+                for h, d in zip(self.out_host, outs):
+                    h[f_off:f_off + nf].copy_(d, non_blocking=True)
+        for s in self.streams:
+            cur.wait_stream(s)
+        cur.synchronize()
+        return self.out_host
+
+    def views(self):
+        lay = self.layout
+        hs = [h.numpy() for h in self.out_host]
+        return [tuple(h[o:o + t] for h in hs) for o, t in zip(lay.frame_offsets, lay.frames)]

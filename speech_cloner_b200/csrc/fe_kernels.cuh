@@ -22,10 +22,10 @@ struct FeTables {
     const float2* mel_w;       // per bin: (weight into band i(k), weight into band i(k)-1)
     const int32_t* mel_istart; // first bin of mel interval i, i in [0, n_mels + 1]; [n_mels+1] = bins
     const int32_t* mel_chunk;  // band boundaries of the kMaxMelChunks work chunks
-    const float* dct_t;        // DCT-II basis transposed: dct_t[m * n_mfcc_pad + q]
+    const float* dct_e;        // DCT-II rows 0,2,4..  transposed: dct_e[n * ne_pad + q/2],  n < ceil(n_mels/2)
+    const float* dct_o;        // DCT-II rows 1,3,5..  transposed: dct_o[n * ne_pad + (q-1)/2]
     int32_t n_mels;
     int32_t n_mfcc;
-    int32_t n_mfcc_pad;        // n_mfcc rounded up to a multiple of 8
 };
 
 struct FeParams {
@@ -230,11 +230,9 @@ __device__ __forceinline__ void fe_epilogue_a(const float* __restrict__ power, i
         atomicMin(&stat_u->m_min, __float_as_uint(m_min));
     }
     {
-        const int n = nfr * n_mels;
-        for (int e = tid; e < n; e += THREADS) {
-            const int f = e / n_mels;
-            mel_dst[e] = mel_db[f * mel_ld + (e - f * n_mels)];
-        }
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int f = warp; f < nfr; f += THREADS / 32)
+            for (int m = lane; m < n_mels; m += 32) mel_dst[f * n_mels + m] = mel_db[f * mel_ld + m];
     }
 }
 
@@ -281,11 +279,21 @@ k_fe_pass_a(const float* __restrict__ wav, Ragged rg, FeTables tb, FeParams prm,
     {
         const int64_t q0 = (int64_t)t0 * kHop - kNfft / 2;
         const double c = prm.pre_emphasis;
-        for (int i = tid; i < kFeSpan; i += kFeThreads) {
-            const int64_t r = reflect_idx(q0 + i, L);
-            const float cur = gain * __ldg(y + r);
-            const float prev = r > 0 ? gain * __ldg(y + r - 1) : 0.0f;
-            sm.span[i] = (R)((double)cur - c * (double)prev);
+        if (q0 >= 1 && q0 + kFeSpan <= L) {
+            // interior tile: no reflection, no 64-bit modulo (it costs ~150 instructions per sample)
+            const float* __restrict__ src = y + q0;
+            for (int i = tid; i < kFeSpan; i += kFeThreads) {
+                const float cur = gain * __ldg(src + i);
+                const float prev = gain * __ldg(src + i - 1);
+                sm.span[i] = (R)((double)cur - c * (double)prev);
+            }
+        } else {
+            for (int i = tid; i < kFeSpan; i += kFeThreads) {
+                const int64_t r = reflect_idx(q0 + i, L);
+                const float cur = gain * __ldg(y + r);
+                const float prev = r > 0 ? gain * __ldg(y + r - 1) : 0.0f;
+                sm.span[i] = (R)((double)cur - c * (double)prev);
+            }
         }
         if (kF64) {
             for (int i = tid; i < kNfft; i += kFeThreads) {
@@ -336,153 +344,174 @@ k_fe_pass_a(const float* __restrict__ wav, Ragged rg, FeTables tb, FeParams prm,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pass B.  One CTA = 128 consecutive frames of one utterance.
-constexpr int kFbFrames = 128;
+// Pass B.  One CTA = 100 consecutive frames of one utterance.
+//   power dB : top_db clip (:157), min shift + scale (:231), clip (:239), in place, float4
+//   mel dB   : top_db clip (:172), min shift + scale (:235), clip (:240)
+//   MFCC     : DCT-II (:176-179) with the even/odd symmetry of its rows: coefficient q uses
+//              s[n] = x[n] + x[N-1-n] (q even) or d[n] = x[n] - x[N-1-n] (q odd), n < N/2, which
+//              halves the multiply-adds; c0 shift (:221), scale (:224), delta (:226-228), clip (:238)
+constexpr int kFbFrames = 100;
 constexpr int kFbThreads = 256;
+
+struct FbLayout {        // shared-memory carve-up, identical on host and device
+    int half, ne_pad, no_pad, sd_ld, cc_ld;
+    size_t off_e, off_o, off_sd, off_cc, off_c00, bytes;
+};
+__host__ __device__ inline FbLayout fb_layout(int n_mels, int n_mfcc) {
+    FbLayout L;
+    L.half = (n_mels + 1) / 2;
+    L.ne_pad = (((n_mfcc + 1) / 2) + 3) & ~3;      // even coefficients q = 0, 2, ..
+    L.no_pad = L.ne_pad;                            // odd coefficients, same padded count
+    L.sd_ld = L.half | 1;                           // float2 stride, odd => conflict-free
+    L.cc_ld = (2 * L.ne_pad) | 1;
+    size_t o = 0;
+    L.off_e = o;  o += sizeof(float) * L.half * L.ne_pad;
+    L.off_o = o;  o += sizeof(float) * L.half * L.no_pad;
+    L.off_sd = o; o += sizeof(float2) * (kFbFrames + 2) * L.sd_ld;
+    L.off_cc = o; o += sizeof(float) * (kFbFrames + 2) * L.cc_ld;
+    L.off_c00 = o; o += 16;
+    L.bytes = o;
+    return L;
+}
 
 __global__ void __launch_bounds__(kFbThreads)
 k_fe_pass_b(Ragged rg, FeTables tb, FeParams prm, const UttStat* __restrict__ stat,
             const float* __restrict__ mel_raw, float* __restrict__ pdb, float* __restrict__ mel_out,
             float* __restrict__ mfcc_out, int n_bins) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = kFbThreads / 32;
     const int tile = blockIdx.x;
     const int u = find_utt(rg.tile_prefix, rg.n_utts, tile);
     const int t0 = (tile - rg.tile_prefix[u]) * kFbFrames;
     const int T = rg.frame_cnt[u];
     const int nfr = min(kFbFrames, T - t0);
     const UttStat st = stat[u];
-    const int n_mels = tb.n_mels, n_mfcc = tb.n_mfcc, n_pad = tb.n_mfcc_pad;
-    const int mel_ld = n_mels + 1, cc_ld = n_pad + 1;
+    const int n_mels = tb.n_mels, n_mfcc = tb.n_mfcc;
+    const FbLayout L = fb_layout(n_mels, n_mfcc);
+    float* dct_e = reinterpret_cast<float*>(smem_raw + L.off_e);      // [half][ne_pad]
+    float* dct_o = reinterpret_cast<float*>(smem_raw + L.off_o);      // [half][no_pad]
+    float2* sd_s = reinterpret_cast<float2*>(smem_raw + L.off_sd);    // [rows][sd_ld] (s, d)
+    float* cc_s = reinterpret_cast<float*>(smem_raw + L.off_cc);      // [rows][cc_ld] scaled cepstra
+    float* c00_s = reinterpret_cast<float*>(smem_raw + L.off_c00);
 
-    float* dct_s = reinterpret_cast<float*>(smem_raw);               // [n_mels][n_pad]
-    float* mel_s = dct_s + n_mels * n_pad;                           // [kFbFrames + 2][mel_ld]
-    float* cc_s = mel_s + (kFbFrames + 2) * mel_ld;                  // [kFbFrames + 2][cc_ld]
-    float* c00_s = cc_s + (kFbFrames + 2) * cc_ld;                   // [1]
-
-    // ---- power dB: top_db clip (:157), min shift + scale (:231), clip (:239); in place
+    // ---- power dB, in place
     {
         const float hi = db10(fmaxf(__uint_as_float(st.p_max), 1e-10f));
         const float floor_db = hi - 80.0f;
         const float lo = fmaxf(db10(fmaxf(__uint_as_float(st.p_min), 1e-10f)), floor_db);
         const float sub = prm.shift_p ? lo : 0.0f;
         const float mul = prm.shift_p ? prm.p_db_norm_factor : 1.0f;
+        const float cl = prm.clip ? 1.0f : __int_as_float(0x7f800000);
         const int64_t base = (rg.frame_off[u] + t0) * n_bins;
         const int n = nfr * n_bins;
         float* __restrict__ p = pdb + base;
+        int head = 0;
         if ((base & 3) == 0) {
             float4* __restrict__ p4 = reinterpret_cast<float4*>(p);
             const int n4 = n >> 2;
             for (int e = tid; e < n4; e += kFbThreads) {
                 float4 v = p4[e];
-                v.x = mul * (fmaxf(v.x, floor_db) - sub); v.y = mul * (fmaxf(v.y, floor_db) - sub);
-                v.z = mul * (fmaxf(v.z, floor_db) - sub); v.w = mul * (fmaxf(v.w, floor_db) - sub);
-                if (prm.clip) {
-                    v.x = fminf(fmaxf(v.x, -1.f), 1.f); v.y = fminf(fmaxf(v.y, -1.f), 1.f);
-                    v.z = fminf(fmaxf(v.z, -1.f), 1.f); v.w = fminf(fmaxf(v.w, -1.f), 1.f);
-                }
+                v.x = fminf(fmaxf(mul * (fmaxf(v.x, floor_db) - sub), -cl), cl);
+                v.y = fminf(fmaxf(mul * (fmaxf(v.y, floor_db) - sub), -cl), cl);
+                v.z = fminf(fmaxf(mul * (fmaxf(v.z, floor_db) - sub), -cl), cl);
+                v.w = fminf(fmaxf(mul * (fmaxf(v.w, floor_db) - sub), -cl), cl);
                 p4[e] = v;
             }
-            for (int e = (n4 << 2) + tid; e < n; e += kFbThreads) {
-                float v = mul * (fmaxf(p[e], floor_db) - sub);
-                if (prm.clip) v = fminf(fmaxf(v, -1.f), 1.f);
-                p[e] = v;
-            }
-        } else {
-            for (int e = tid; e < n; e += kFbThreads) {
-                float v = mul * (fmaxf(p[e], floor_db) - sub);
-                if (prm.clip) v = fminf(fmaxf(v, -1.f), 1.f);
-                p[e] = v;
-            }
+            head = n4 << 2;
         }
+        for (int e = head + tid; e < n; e += kFbThreads)
+            p[e] = fminf(fmaxf(mul * (fmaxf(p[e], floor_db) - sub), -cl), cl);
     }
 
-    // ---- mel dB rows t0-1 .. t0+nfr (halo for the delta), top_db clip (:172)
+    // ---- mel dB rows t0-1 .. t0+nfr (halo for the delta): clip, write the normalised rows, build (s, d)
     const float m_hi = 2.0f * db10(fmaxf(__uint_as_float(st.m_max), 1e-5f));
     const float m_floor = m_hi - 80.0f;
     const float m_lo = fmaxf(2.0f * db10(fmaxf(__uint_as_float(st.m_min), 1e-5f)), m_floor);
     {
         const float* __restrict__ src = mel_raw + rg.frame_off[u] * n_mels;
-        const int n = (nfr + 2) * n_mels;
-        for (int e = tid; e < n; e += kFbThreads) {
-            const int r = e / n_mels;
+        float* __restrict__ dst = mel_out + rg.frame_off[u] * n_mels;
+        const float sub = prm.shift_m ? m_lo : 0.0f;
+        const float mul = prm.shift_m ? prm.m_db_norm_factor : 1.0f;
+        const float cl = prm.clip ? 1.0f : __int_as_float(0x7f800000);
+        const int pairs = n_mels / 2;
+        for (int r = warp; r < nfr + 2; r += kWarps) {
             const int t = t0 - 1 + r;
-            const int m = e - r * n_mels;
-            float v = 0.f;
-            if (t >= 0 && t < T) v = fmaxf(__ldg(src + (int64_t)t * n_mels + m), m_floor);
-            mel_s[r * mel_ld + m] = v;
+            const bool ok = t >= 0 && t < T;
+            const bool own = r >= 1 && r <= nfr;
+            for (int n = lane; n < L.half; n += 32) {
+                float a = 0.f, b = 0.f;
+                if (ok) {
+                    a = fmaxf(__ldg(src + (int64_t)t * n_mels + n), m_floor);
+                    if (n < pairs) b = fmaxf(__ldg(src + (int64_t)t * n_mels + (n_mels - 1 - n)), m_floor);
+                    if (own) {
+                        dst[(int64_t)t * n_mels + n] = fminf(fmaxf(mul * (a - sub), -cl), cl);
+                        if (n < pairs) dst[(int64_t)t * n_mels + (n_mels - 1 - n)] = fminf(fmaxf(mul * (b - sub), -cl), cl);
+                    }
+                }
+                sd_s[r * L.sd_ld + n] = n < pairs ? make_float2(a + b, a - b) : make_float2(a, 0.f);
+            }
         }
-        for (int e = tid; e < n_mels * n_pad; e += kFbThreads) dct_s[e] = tb.dct_t[e];
+        for (int e = tid; e < L.half * L.ne_pad; e += kFbThreads) { dct_e[e] = tb.dct_e[e]; dct_o[e] = tb.dct_o[e]; }
         // MFCC[0, 0] of the utterance (:221): first DCT row applied to frame 0
-        if (tid < 32) {
+        if (warp == kWarps - 1) {
             float a = 0.f;
             if (prm.norm_first)
-                for (int m = tid; m < n_mels; m += 32)
-                    a = fmaf(__ldg(tb.dct_t + m * n_pad), fmaxf(__ldg(src + m), m_floor), a);
+                for (int n = lane; n < L.half; n += 32) {
+                    const float x1 = fmaxf(__ldg(src + n), m_floor);
+                    const float x2 = n < pairs ? fmaxf(__ldg(src + (n_mels - 1 - n)), m_floor) : 0.f;
+                    a = fmaf(__ldg(tb.dct_e + n * L.ne_pad), x1 + x2, a);
+                }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (tid == 0) c00_s[0] = a;
+            if (lane == 0) c00_s[0] = a;
         }
     }
     __syncthreads();
 
-    // ---- normalised mel output (:235, :240)
+    // ---- DCT: task = (row, group of 4 even + 4 odd coefficients); lanes = consecutive rows
     {
-        const float sub = prm.shift_m ? m_lo : 0.0f;
-        const float mul = prm.shift_m ? prm.m_db_norm_factor : 1.0f;
-        float* __restrict__ dst = mel_out + (rg.frame_off[u] + t0) * n_mels;
-        const int n = nfr * n_mels;
-        for (int e = tid; e < n; e += kFbThreads) {
-            const int r = e / n_mels;
-            float v = mul * (mel_s[(r + 1) * mel_ld + (e - r * n_mels)] - sub);
-            if (prm.clip) v = fminf(fmaxf(v, -1.f), 1.f);
-            dst[e] = v;
-        }
-    }
-    // ---- DCT-II (:176-179), c0 shift (:221), scale (:224): task = (frame row, group of 8 coefficients)
-    {
-        const int groups = n_pad >> 3;
+        const int groups = L.ne_pad >> 2;
         const int rows = nfr + 2;
         const float c00 = c00_s[0];
+        const float sc = prm.mfcc_norm_factor;
         for (int task = tid; task < rows * groups; task += kFbThreads) {
             const int g = task / rows;
             const int r = task - g * rows;
-            const float* __restrict__ x = mel_s + r * mel_ld;
-            const float4* __restrict__ d = reinterpret_cast<const float4*>(dct_s + 8 * g);
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int m = 0; m < n_mels; ++m) {
-                const float xv = x[m];
-                const float4 d0 = d[(m * n_pad) >> 2], d1 = d[((m * n_pad) >> 2) + 1];
-                acc[0] = fmaf(d0.x, xv, acc[0]); acc[1] = fmaf(d0.y, xv, acc[1]);
-                acc[2] = fmaf(d0.z, xv, acc[2]); acc[3] = fmaf(d0.w, xv, acc[3]);
-                acc[4] = fmaf(d1.x, xv, acc[4]); acc[5] = fmaf(d1.y, xv, acc[5]);
-                acc[6] = fmaf(d1.z, xv, acc[6]); acc[7] = fmaf(d1.w, xv, acc[7]);
+            const float2* __restrict__ x = sd_s + r * L.sd_ld;
+            const float4* __restrict__ e4 = reinterpret_cast<const float4*>(dct_e + 4 * g);
+            const float4* __restrict__ o4 = reinterpret_cast<const float4*>(dct_o + 4 * g);
+            const int ld4 = L.ne_pad >> 2;
+            float ae0 = 0.f, ae1 = 0.f, ae2 = 0.f, ae3 = 0.f, ao0 = 0.f, ao1 = 0.f, ao2 = 0.f, ao3 = 0.f;
+#pragma unroll 4
+            for (int n = 0; n < L.half; ++n) {
+                const float2 v = x[n];
+                const float4 e = e4[n * ld4], o = o4[n * ld4];
+                ae0 = fmaf(e.x, v.x, ae0); ae1 = fmaf(e.y, v.x, ae1); ae2 = fmaf(e.z, v.x, ae2); ae3 = fmaf(e.w, v.x, ae3);
+                ao0 = fmaf(o.x, v.y, ao0); ao1 = fmaf(o.y, v.y, ao1); ao2 = fmaf(o.z, v.y, ao2); ao3 = fmaf(o.w, v.y, ao3);
             }
-            if (g == 0) acc[0] -= c00;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cc_s[r * cc_ld + 8 * g + i] = prm.mfcc_norm_factor * acc[i];
+            if (g == 0) ae0 -= c00;
+            float* __restrict__ c = cc_s + r * L.cc_ld + 8 * g;
+            c[0] = sc * ae0; c[1] = sc * ao0; c[2] = sc * ae1; c[3] = sc * ao1;
+            c[4] = sc * ae2; c[5] = sc * ao2; c[6] = sc * ae3; c[7] = sc * ao3;
         }
     }
     __syncthreads();
-    // ---- MFCC (+ delta, :226-228) output, clip (:238)
+    // ---- MFCC (+ delta) output
     {
         const int width = prm.use_delta ? 2 * n_mfcc : n_mfcc;
+        const float cl = prm.clip ? 1.0f : __int_as_float(0x7f800000);
         float* __restrict__ dst = mfcc_out + (rg.frame_off[u] + t0) * width;
-        const int n = nfr * width;
-        for (int e = tid; e < n; e += kFbThreads) {
-            const int r = e / width;
-            const int q = e - r * width;
+        for (int r = warp; r < nfr; r += kWarps) {
             const int t = t0 + r;
-            float v;
-            if (q < n_mfcc) {
-                v = cc_s[(r + 1) * cc_ld + q];
-            } else if (t == 0 || t == T - 1) {
-                v = 0.f;
-            } else {
-                v = 2.0f * (cc_s[(r + 2) * cc_ld + (q - n_mfcc)] - cc_s[r * cc_ld + (q - n_mfcc)]);
+            const bool edge = (t == 0 || t == T - 1);
+            for (int q = lane; q < width; q += 32) {
+                float v;
+                if (q < n_mfcc) v = cc_s[(r + 1) * L.cc_ld + q];
+                else if (edge) v = 0.f;
+                else v = 2.0f * (cc_s[(r + 2) * L.cc_ld + (q - n_mfcc)] - cc_s[r * L.cc_ld + (q - n_mfcc)]);
+                dst[r * width + q] = fminf(fmaxf(v, -cl), cl);
             }
-            if (prm.clip) v = fminf(fmaxf(v, -1.f), 1.f);
-            dst[e] = v;
         }
     }
 }

@@ -43,13 +43,15 @@ struct GlTables {
 
 // 1 / window_sumsquare at padded position p (librosa 0.6 filters.window_sumsquare, float32
 // accumulator receiving float64 terms in ascending frame order); 1 where the sum is <= tiny.
-__device__ __forceinline__ float inv_wss_at(int64_t p, int T, const GlTables& tb) {
-    int64_t lo = p >= kNfft ? (p - kNfft) / kHop + 1 : 0;
-    int64_t hi = p / kHop;
+// Positions are 32-bit (signals up to 2^31 samples, checked on the host): 64-bit divisions cost
+// ~100 instructions each on the GPU and used to dominate this kernel.
+__device__ __forceinline__ float inv_wss_at(int p, int T, const GlTables& tb) {
+    const int lo = p >= kNfft ? (p - kNfft) / kHop + 1 : 0;
+    int hi = p / kHop;
     if (hi > T - 1) hi = T - 1;
-    if (hi - lo == kNfft / kHop - 1) return __ldg(tb.inv_wss + (int)(p % kHop));
+    if (hi - lo == kNfft / kHop - 1) return __ldg(tb.inv_wss + (p % kHop));
     float acc = 0.f;
-    for (int64_t i = lo; i <= hi; ++i) acc = (float)((double)acc + __ldg(tb.win_sq + (int)(p - i * kHop)));
+    for (int i = lo; i <= hi; ++i) acc = (float)((double)acc + __ldg(tb.win_sq + (p - i * kHop)));
     return acc > 1.1754944e-38f ? 1.0f / acc : 1.0f;
 }
 
@@ -71,13 +73,14 @@ k_gl_iter(const GlJob* __restrict__ jobs, int n_jobs, const int32_t* __restrict_
     const int ji = find_utt(tile_prefix, n_jobs, blockIdx.x);
     const GlJob job = jobs[ji];
     const int T = job.T;
-    const int64_t Lw = (int64_t)kHop * (T - 1);               // whole-signal length
+    const int Lw = kHop * (T - 1);                            // whole-signal length (< 2^31, host-checked)
     // tiles sit on a whole-signal grid of kGlOut padded samples (padded = trimmed + 200), so a
     // time-chunked run pairs and sums frames exactly like the unchunked one (bit-identical)
-    const int64_t p_first = ((job.out_first + kNfft / 2) / kGlOut) * kGlOut;
-    const int64_t o = p_first + (int64_t)(blockIdx.x - job.tile0) * kGlOut;
-    const int64_t t0 = o / kHop - 4;                           // first frame of the tile
-    const int64_t span0 = t0 * kHop;                           // padded position of span[0]
+    const int out_first = (int)job.out_first, out_end = (int)(job.out_first + job.out_count);
+    const int p_first = ((out_first + kNfft / 2) / kGlOut) * kGlOut;
+    const int o = p_first + (int)(blockIdx.x - job.tile0) * kGlOut;
+    const int t0 = o / kHop - 4;                               // first frame of the tile
+    const int span0 = t0 * kHop;                               // padded position of span[0]
 
     for (int i = tid; i < kNfft; i += kFeThreads) {
         sm.win_half[i] = tb.win_half[i];
@@ -85,9 +88,16 @@ k_gl_iter(const GlJob* __restrict__ jobs, int n_jobs, const int32_t* __restrict_
     }
     if (!INIT) {
         const float* __restrict__ src = wav_in + job.wav_in_off;
-        for (int i = tid; i < kGlSpan; i += kFeThreads) {
-            const int64_t r = reflect_idx(span0 + i - kNfft / 2, Lw) - job.wav_in_first;
-            sm.span[i] = (r >= 0 && r < job.wav_in_count) ? __ldg(src + r) : 0.0f;
+        const int q0 = span0 - kNfft / 2;                      // whole-signal index of span[0]
+        const int in_first = (int)job.wav_in_first, in_end = (int)(job.wav_in_first + job.wav_in_count);
+        if (q0 >= 0 && q0 + kGlSpan <= Lw && q0 >= in_first && q0 + kGlSpan <= in_end) {
+            const float* __restrict__ s0 = src + (q0 - in_first);       // interior tile: plain copy
+            for (int i = tid; i < kGlSpan; i += kFeThreads) sm.span[i] = __ldg(s0 + i);
+        } else {
+            for (int i = tid; i < kGlSpan; i += kFeThreads) {
+                const int r = (int)reflect_idx((int64_t)q0 + i, Lw) - in_first;
+                sm.span[i] = (r >= 0 && r < in_end - in_first) ? __ldg(src + r) : 0.0f;
+            }
         }
     }
     const int unit = tid / kUnitThreads;
@@ -101,9 +111,9 @@ k_gl_iter(const GlJob* __restrict__ jobs, int n_jobs, const int32_t* __restrict_
     // holds) is fed exact zeros end to end: the two frames of a pair share one packed transform, so
     // any garbage in the partner would change the rounding of the real frame and break the
     // bit-identity of time-chunked runs.
-    const int64_t fa = t0 + 2 * unit, fb = fa + 1;
-    const bool va = fa >= job.f_lo && fa < (int64_t)job.f_lo + job.f_cnt && fa < T;
-    const bool vb = fb >= job.f_lo && fb < (int64_t)job.f_lo + job.f_cnt && fb < T;
+    const int fa = t0 + 2 * unit, fb = fa + 1;
+    const bool va = fa >= job.f_lo && fa < job.f_lo + job.f_cnt && fa < T;
+    const bool vb = fb >= job.f_lo && fb < job.f_lo + job.f_cnt && fb < T;
     const float ka = va ? 1.0f : 0.0f, kb = vb ? 1.0f : 0.0f;
     if (!INIT) {
         float s[24];
@@ -158,18 +168,20 @@ k_gl_iter(const GlJob* __restrict__ jobs, int n_jobs, const int32_t* __restrict_
     // ---- ordered overlap-add gather + normalisation; local positions [320, 320 + kGlOut) are complete
     {
         float* __restrict__ dst = wav_out + job.wav_out_off;
-        const int64_t out_end = job.out_first + job.out_count;
+        // every output sample of an interior tile is covered by all 5 frames: periodic 1 / sum-square
+        const bool steady = t0 >= 0 && t0 + kGlFrames <= T;
         for (int i = tid; i < kGlOut; i += kFeThreads) {
             const int l = 320 + i;                                  // local padded offset in the tile
-            const int64_t p = span0 + l;                            // padded position
-            const int64_t s = p - kNfft / 2;                        // whole-signal sample index
-            if (s < job.out_first || s >= out_end || s >= Lw) continue;
+            const int p = span0 + l;                                // padded position
+            const int s = p - kNfft / 2;                            // whole-signal sample index
+            if (s < out_first || s >= out_end || s >= Lw) continue;
             int u_lo = l >= kGlSeg ? (l - kGlSeg) / (2 * kHop) + 1 : 0;
             int u_hi = l / (2 * kHop);
             if (u_hi > kFeUnits - 1) u_hi = kFeUnits - 1;
             float acc = 0.f;
             for (int uu = u_lo; uu <= u_hi; ++uu) acc += seg[uu * kGlSeg + (l - uu * 2 * kHop)];
-            dst[s - job.out_first] = acc * inv_wss_at(p, T, tb);
+            const float nrm = steady ? __ldg(tb.inv_wss + (l % kHop)) : inv_wss_at(p, T, tb);
+            dst[s - out_first] = acc * nrm;
         }
     }
 }

@@ -100,8 +100,8 @@ struct sc_plan {
     const float2* mel_w = nullptr;
     const int32_t* mel_istart = nullptr;
     const int32_t* mel_chunk = nullptr;
-    const float* dct_t = nullptr;
-    int n_mfcc_pad = 0;
+    const float* dct_e = nullptr;
+    const float* dct_o = nullptr;
     // generic-size tables
     const double* g_fe_win = nullptr;    // analysis window (n_fft), float64
     const float* g_gl_win = nullptr;     // hann (n_fft)
@@ -114,6 +114,11 @@ struct sc_plan {
     // per-call workspaces
     DescStage ds;
     DevBuf work, work2;
+    // optional per-kernel timing (bench.py's roofline): events recorded on the caller's stream
+    bool profile = false;
+    cudaEvent_t pev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int pev_kind = 0;        // 1 = front-end (gain | pass A | pass B), 2 = Griffin-Lim (init | iterations)
+    int pev_iters = 0;
 };
 
 static int upload_blob(DescStage& ds, const Blob& b, cudaStream_t st) {
@@ -278,18 +283,20 @@ extern "C" int sc_plan_create(const sc_params* p, sc_plan** out) {
     }
     std::vector<float> inv_wss = build_inv_wss(pl->gl_window, n_fft, p->hop_length);
     MelSparse ms = build_mel(p->sample_rate, n_fft, p->n_mels);
-    pl->n_mfcc_pad = (p->n_mfcc + 7) & ~7;
-    std::vector<float> dct((size_t)p->n_mels * pl->n_mfcc_pad, 0.f);
+    // librosa.filters.dct (audio_lib.py:176): row 0 = 1/sqrt(N), row q = sqrt(2/N) cos(q (2n+1) pi / 2N),
+    // split into even / odd rows over the first half of the inputs (see k_fe_pass_b)
+    const FbLayout fbl = fb_layout(p->n_mels, p->n_mfcc);
+    std::vector<float> dct_e((size_t)fbl.half * fbl.ne_pad, 0.f), dct_o((size_t)fbl.half * fbl.no_pad, 0.f);
     for (int q = 0; q < p->n_mfcc; ++q)
-        for (int m = 0; m < p->n_mels; ++m) {
-            // librosa.filters.dct (audio_lib.py:176): row 0 = 1/sqrt(n), row q = sqrt(2/n) cos(q (2m+1) pi / 2n)
+        for (int m = 0; m < fbl.half; ++m) {
             const double v = q == 0 ? 1.0 / sqrt((double)p->n_mels)
                                     : cos(q * (2.0 * m + 1.0) * M_PI / (2.0 * p->n_mels)) * sqrt(2.0 / p->n_mels);
-            dct[(size_t)m * pl->n_mfcc_pad + q] = (float)v;
+            if (q & 1) dct_o[(size_t)m * fbl.no_pad + q / 2] = (float)v;
+            else dct_e[(size_t)m * fbl.ne_pad + q / 2] = (float)v;
         }
     const size_t o_wn = b.add(wn), o_feh = b.add(fe_half), o_glh = b.add(gl_half), o_gli = b.add(gl_inv);
     const size_t o_sq = b.add(gl_sq), o_wss = b.add(inv_wss), o_mw = b.add(ms.w), o_mi = b.add(ms.istart);
-    const size_t o_mc = b.add(ms.chunk), o_dct = b.add(dct), o_few = b.add(pl->fe_window), o_glw = b.add(gl_w);
+    const size_t o_mc = b.add(ms.chunk), o_dcte = b.add(dct_e), o_dcto = b.add(dct_o), o_few = b.add(pl->fe_window), o_glw = b.add(gl_w);
     const size_t o_wnd = b.add(wn_d), o_fehd = b.add(fe_half_d);
     std::vector<float> zeros(pl->n_bins, 0.f);
     const size_t o_zero = b.add(zeros);
@@ -313,7 +320,8 @@ extern "C" int sc_plan_create(const sc_params* p, sc_plan** out) {
     pl->mel_w = (const float2*)(base + o_mw);
     pl->mel_istart = (const int32_t*)(base + o_mi);
     pl->mel_chunk = (const int32_t*)(base + o_mc);
-    pl->dct_t = (const float*)(base + o_dct);
+    pl->dct_e = (const float*)(base + o_dcte);
+    pl->dct_o = (const float*)(base + o_dcto);
     pl->g_fe_win = (const double*)(base + o_few);
     pl->g_gl_win = (const float*)(base + o_glw);
     *out = pl;
@@ -323,6 +331,7 @@ extern "C" int sc_plan_create(const sc_params* p, sc_plan** out) {
 extern "C" void sc_plan_destroy(sc_plan* pl) {
     if (!pl) return;
     pl->ds.release();
+    for (auto& e : pl->pev) if (e) cudaEventDestroy(e);
     pl->tables.release(); pl->work.release(); pl->work2.release();
     delete pl;
 }
@@ -335,8 +344,8 @@ static FeTables fe_tables(const sc_plan* pl) {
     FeTables t;
     t.w400 = pl->w400; t.win_half = pl->fe_win_half; t.w400_d = pl->w400_d; t.win_half_d = pl->fe_win_half_d;
     t.mel_w = pl->mel_w; t.mel_istart = pl->mel_istart;
-    t.mel_chunk = pl->mel_chunk; t.dct_t = pl->dct_t;
-    t.n_mels = pl->prm.n_mels; t.n_mfcc = pl->prm.n_mfcc; t.n_mfcc_pad = pl->n_mfcc_pad;
+    t.mel_chunk = pl->mel_chunk; t.dct_e = pl->dct_e; t.dct_o = pl->dct_o;
+    t.n_mels = pl->prm.n_mels; t.n_mfcc = pl->prm.n_mfcc;
     return t;
 }
 static FeParams fe_params(const sc_plan* pl) {
@@ -411,6 +420,7 @@ extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* s
     const FeTables tb = fe_tables(pl);
     const FeParams fp = fe_params(pl);
 
+    if (pl->profile) { SC_CUDA(cudaEventRecord(pl->pev[0], st)); pl->pev_kind = 1; }
     if (fp.use_gain) {
         rg.tile_prefix = at<int32_t>(pl, o_pabs);
         k_abs_pairwise<<<pre_abs[n], kAbsThreads, 0, st>>>(wav, rg, at<int64_t>(pl, o_heap), heap);
@@ -420,6 +430,7 @@ extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* s
     k_gain_finalize<<<(n + 3) / 4, 128, 0, st>>>(rg, at<int64_t>(pl, o_heap), heap, stat, fp.mean_abs_amp_norm, fp.use_gain, nullptr);
     SC_LAUNCHED();
 
+    if (pl->profile) SC_CUDA(cudaEventRecord(pl->pev[1], st));
     rg.tile_prefix = at<int32_t>(pl, o_pa);
     if (pl->fast) {
         static bool attr_set = false;
@@ -441,15 +452,15 @@ extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* s
         k_gen_fe_pass_a<<<pre_a[n], kGenThreads, smem, st>>>(wav, rg, gt, tb, fp, stat, pdb, mel_raw);
         SC_LAUNCHED();
     }
+    if (pl->profile) SC_CUDA(cudaEventRecord(pl->pev[2], st));
     rg.tile_prefix = at<int32_t>(pl, o_pb);
     {
-        const int n_mels = pl->prm.n_mels, n_pad = pl->n_mfcc_pad;
-        const size_t smem = sizeof(float) * ((size_t)n_mels * n_pad + (kFbFrames + 2) * (n_mels + 1) +
-                                             (kFbFrames + 2) * (n_pad + 1) + 4);
+        const size_t smem = fb_layout(pl->prm.n_mels, pl->prm.n_mfcc).bytes;
         SC_CUDA(cudaFuncSetAttribute(k_fe_pass_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_fe_pass_b<<<pre_b[n], kFbThreads, smem, st>>>(rg, tb, fp, stat, mel_raw, pdb, mel, mfcc, pl->n_bins);
         SC_LAUNCHED();
     }
+    if (pl->profile) SC_CUDA(cudaEventRecord(pl->pev[3], st));
     return SC_OK;
 }
 
@@ -652,7 +663,8 @@ extern "C" int sc_griffinlim_batch(sc_plan* pl, const float* amp, const float* p
     int64_t total = 0;
     for (int u = 0; u < n; ++u) {
         const int64_t T = fcnt_in ? fcnt_in[u] : foff[u + 1] - foff[u];
-        if (T < 1 || T > INT32_MAX / 2) return fail(SC_ERR_INVALID, "sc_griffinlim_batch: bad frame count");
+        if (T < 1 || (int64_t)hop * T + pl->prm.n_fft >= INT32_MAX)
+            return fail(SC_ERR_INVALID, "sc_griffinlim_batch: bad frame count (signal must stay below 2^31 samples)");
         GlJob& j = jobs[u];
         j.amp_row0 = foff[u];
         j.wav_in_off = soff[u]; j.wav_in_first = 0; j.wav_in_count = (int64_t)hop * (T - 1);
@@ -676,7 +688,9 @@ extern "C" int sc_griffinlim_batch(sc_plan* pl, const float* amp, const float* p
     const int32_t* dp = at<int32_t>(pl, o_p);
     // iteration i writes buffer (n_iters - 1 - i) & 1 ? other : wav, so the last one lands in `wav`
     auto buf = [&](int i) { return ((n_iters - 1 - i) & 1) ? other : wav; };
+    if (pl->profile) { SC_CUDA(cudaEventRecord(pl->pev[0], st)); pl->pev_kind = 2; pl->pev_iters = n_iters; }
     if (int rc = gl_launch(pl, true, dj, n, dp, prefix[n], amp, phase0, nullptr, buf(0), st)) return rc;
+    if (pl->profile) SC_CUDA(cudaEventRecord(pl->pev[1], st));
     for (int i = 1; i < n_iters; ++i) {
         if (int rc = gl_launch(pl, false, dj, n, dp, prefix[n], amp, phase0, buf(i - 1), buf(i), st)) return rc;
         if (rms && rprefix[n] > 0) {
@@ -686,6 +700,7 @@ extern "C" int sc_griffinlim_batch(sc_plan* pl, const float* amp, const float* p
             SC_LAUNCHED();
         }
     }
+    if (pl->profile) SC_CUDA(cudaEventRecord(pl->pev[2], st));
     return SC_OK;
 }
 
@@ -695,7 +710,7 @@ extern "C" int sc_griffinlim_chunk_step(sc_plan* pl, const float* amp, const flo
                                         void* stream) {
     if (!pl || !amp || !wav_out) return fail(SC_ERR_INVALID, "sc_griffinlim_chunk_step: null argument");
     if (!phase0 && !wav_in) return fail(SC_ERR_INVALID, "sc_griffinlim_chunk_step: need phase0 or wav_in");
-    if (n_total < 1 || n_total > INT32_MAX / 2 || n_local < 0 || first_frame < 0 || first_frame + n_local > n_total)
+    if (n_total < 1 || (int64_t)pl->prm.hop_length * n_total + pl->prm.n_fft >= INT32_MAX || n_local < 0 || first_frame < 0 || first_frame + n_local > n_total)
         return fail(SC_ERR_INVALID, "sc_griffinlim_chunk_step: bad frame range");
     const int64_t Lw = (int64_t)pl->prm.hop_length * (n_total - 1);
     if (out_first < 0 || out_count < 0 || out_first + out_count > Lw)
@@ -727,6 +742,31 @@ extern "C" int sc_transpose_to_f32(const void* src, int32_t is_f64, int64_t rows
     else
         k_transpose<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, rows, cols, dst);
     SC_LAUNCHED();
+    return SC_OK;
+}
+
+extern "C" int sc_profile_enable(sc_plan* pl, int32_t on) {
+    if (!pl) return fail(SC_ERR_INVALID, "sc_profile_enable: null plan");
+    if (on)
+        for (auto& e : pl->pev)
+            if (!e) SC_CUDA(cudaEventCreate(&e));
+    pl->profile = on != 0;
+    pl->pev_kind = 0;
+    return SC_OK;
+}
+
+extern "C" int sc_profile_read(sc_plan* pl, double* ms_out) {
+    if (!pl || !ms_out) return fail(SC_ERR_INVALID, "sc_profile_read: null argument");
+    for (int i = 0; i < 4; ++i) ms_out[i] = 0.0;
+    if (!pl->profile || pl->pev_kind == 0) return fail(SC_ERR_INVALID, "sc_profile_read: nothing recorded");
+    const int last = pl->pev_kind == 1 ? 3 : 2;
+    SC_CUDA(cudaEventSynchronize(pl->pev[last]));
+    for (int i = 0; i < last; ++i) {
+        float ms = 0.f;
+        SC_CUDA(cudaEventElapsedTime(&ms, pl->pev[i], pl->pev[i + 1]));
+        ms_out[i] = ms;
+    }
+    ms_out[3] = pl->pev_kind == 2 ? (double)pl->pev_iters : 0.0;
     return SC_OK;
 }
 

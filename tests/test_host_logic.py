@@ -1,0 +1,67 @@
+"""Host-side logic of the Python mirror that needs no GPU: layouts, validation order, plan keys."""
+import numpy as np
+import pytest
+
+from speech_cloner_b200 import audio_lib as al
+from speech_cloner_b200 import synth
+
+
+def test_frontend_layout_alignment_and_counts():
+    lens = [48000, 16001, 7999, 81, 80, 79, 1]
+    lay = al.FrontendLayout(lens, 80)
+    assert lay.frames == [1 + n // 80 for n in lens] == [601, 201, 100, 2, 2, 1, 1]
+    assert all(o % 4 == 0 for o in lay.sample_offsets + lay.frame_offsets)        # 16-byte aligned rows
+    for i, n in enumerate(lens):
+        assert lay.sample_offsets[i + 1] - lay.sample_offsets[i] >= n
+        assert lay.frame_offsets[i + 1] - lay.frame_offsets[i] >= lay.frames[i]
+    assert list(lay.c_sample_lengths) == lens
+
+
+def test_gl_layout():
+    lay = al._GlLayout([1000, 2, 301], 80)
+    assert lay.samples == [79920, 80, 24000]
+    assert all(o % 4 == 0 for o in lay.sample_offsets + lay.frame_offsets)
+
+
+def test_validation_happens_before_any_device_work():
+    hp = dict(synth.HP_ENC)
+    for bad in ([0.0, 1.0], np.zeros(10, dtype=np.int32), np.zeros((2, 8), dtype=np.float32),
+                np.array([], dtype=np.float32), np.array([0.0, np.inf], dtype=np.float32)):
+        with pytest.raises(ValueError):
+            al.calc_MFCC_input(bad, **hp)
+
+
+def test_window_array_matches_scipy():
+    from scipy import signal
+    np.testing.assert_array_equal(al._window_array("hann", 400), signal.get_window("hann", 400, fftbins=True))
+    np.testing.assert_array_equal(al._window_array("hamm", 400), signal.get_window("hamming", 400, fftbins=True))
+    np.testing.assert_array_equal(al._window_array(("kaiser", 4.0), 64), signal.get_window(("kaiser", 4.0), 64))
+    with pytest.raises(ValueError):
+        al._window_array(np.ones(5), 400)
+
+
+def test_signatures_match_reference():
+    """Positional order and defaults of the five reference functions (audio_lib.py:12, :31, :89-104, :249, :278-287)."""
+    import inspect
+    sig = lambda f: [(p.name, p.default) for p in inspect.signature(f).parameters.values()]
+    E = inspect.Parameter.empty
+    assert sig(al.calc_preemphasis) == [("wav", E), ("coeff", 0.97)]
+    assert sig(al.calc_inv_preemphasis) == [("preem_wav", E), ("coeff", 0.97)]
+    assert sig(al.calc_PHN_target) == [("y", E), ("phn_v", E), ("phn_conv_d", E), ("hop_length", 40), ("win_length", 400)]
+    assert sig(al.calc_MFCC_input) == [
+        ("y", E), ("sr", 16000), ("pre_emphasis", 0.97), ("hop_length", 40), ("win_length", 400), ("n_mels", 128),
+        ("n_mfcc", 40), ("n_fft", None), ("window", "hann"), ("mfcc_normaleze_first_mfcc", True),
+        ("mfcc_norm_factor", 0.01), ("calc_mfcc_derivate", False), ("M_dB_norm_factor", 0.01),
+        ("P_dB_norm_factor", 0.01), ("mean_abs_amp_norm", 0.003), ("clip_output", True)]
+    assert sig(al.griffin_lim_alg)[:6] == [("stft_amp", E), ("win_length", E), ("hop_length", E), ("num_iters", 300),
+                                           ("n_fft", None), ("verbose", True)]
+    assert sig(al.from_power_to_wav)[:10] == [
+        ("P", E), ("P_dB_norm_factor", 0.01), ("pre_emphasis", 0.97), ("hop_length", 40), ("win_length", 800),
+        ("mean_abs_amp_norm", 0.01), ("n_iter", 200), ("n_fft", None), ("realse", 1.0), ("verbose", True)]
+
+
+def test_synth_is_seeded_and_shaped():
+    a, b = synth.utterance(7, 1.0), synth.utterance(7, 1.0)
+    np.testing.assert_array_equal(a, b)
+    assert a.dtype == np.float32 and a.shape == (16000,) and 0.05 < np.abs(a).max() < 0.2
+    assert np.abs(synth.utterance(7, 1.0, ds_norm=(0.0, 10.0)) - 10 * a).max() < 1e-6
