@@ -31,7 +31,24 @@ struct Ragged {
     const int32_t* frame_cnt;    // frames of utterance u
     const int32_t* tile_prefix;  // exclusive prefix sum of tiles per utterance (n_utts + 1)
     int32_t n_utts;
+    // pass A splits an utterance's tiles into interior tiles [int_first, int_first + int_count), whose
+    // samples need no reflect padding (persistent cp.async kernel), and edge tiles (plain kernel)
+    const int32_t* int_first;
+    const int32_t* int_count;
 };
+
+// ---- asynchronous global -> shared copies (LDGSTS) and named barriers
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <int ID, int COUNT> __device__ __forceinline__ void bar_sync() {
+    if (ID == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
+}
 
 // largest u with prefix[u] <= tile
 __device__ __forceinline__ int find_utt(const int32_t* __restrict__ prefix, int n, int tile) {

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(128) k_gain_finalize(Ragged rg, const int64_t*
 //   raw power dB (:157 without the top_db clip)  -> pdb_dst  (coalesced)
 //   sparse Slaney mel (:160-169) + raw amplitude_to_db (:172) -> mel_dst
 //   utterance max / min of the power and of the mel power   -> stat (order-independent atomics)
-template <int THREADS>
+template <int THREADS, int BAR = 0>
 __device__ __forceinline__ void fe_epilogue_a(const float* __restrict__ power, int F, int bins, int nfr,
                                               const float2* __restrict__ mel_w_s, const int32_t* __restrict__ istart_s,
                                               const FeTables& tb, float* __restrict__ mel_db,
@@ -218,7 +218,7 @@ __device__ __forceinline__ void fe_epilogue_a(const float* __restrict__ power, i
         red[0][tid >> 5] = p_max; red[1][tid >> 5] = p_min;
         red[2][tid >> 5] = m_max; red[3][tid >> 5] = m_min;
     }
-    __syncthreads();
+    bar_sync<BAR, THREADS>();
     if (tid == 0) {
         for (int w = 1; w < THREADS / 32; ++w) {
             p_max = fmaxf(p_max, red[0][w]); p_min = fminf(p_min, red[1][w]);
@@ -243,33 +243,41 @@ __device__ __forceinline__ void fe_epilogue_a(const float* __restrict__ power, i
 template <typename R> struct FeTw { using type = TwReg<float>; };
 template <> struct FeTw<double> { using type = TwTab<double>; };
 
-template <typename R>
+template <typename R, int UNITS>
 struct FeSmemA {
-    R span[kFeSpan];                           // pre-emphasised, reflect-padded samples of the tile
+    static constexpr int F = 2 * UNITS;                  // frames per tile
+    static constexpr int SPAN = kHop * (F - 1) + kNfft;  // samples a tile touches
+    static constexpr int THREADS = UNITS * kUnitThreads;
+    R span[SPAN];                              // pre-emphasised, reflect-padded samples of the tile
     R win[kNfft];
-    cx<R> slots[kFeUnits * kUnitSlots];        // step-1 -> step-2 exchange
+    cx<R> slots[UNITS * kUnitSlots];           // step-1 -> step-2 exchange
     cx<R> w400[sizeof(R) == 8 ? kNfft : 1];    // twiddle table (float64 path reads it on use)
-    float power[kFeFrames * kBins];            // |X|^2, row = frame
+    float power[F * kBins];                    // |X|^2, row = frame
     float2 mel_w[kBins];
     int32_t mel_istart[kMaxMels + 2];
-    float red[4][kFeThreads / 32];
-    // followed by mel_db[kFeFrames][n_mels + 1]
+    float red[4][(THREADS + 31) / 32];
+    // followed by mel_db[F][n_mels + 1]
 };
 
-template <typename R>
-__global__ void __launch_bounds__(kFeThreads, sizeof(R) == 8 ? 1 : 2)
+// Plain (one tile per CTA) pass A.  Handles any tile, including those that need reflect padding;
+// with rg.int_first set it runs only the EDGE tiles of each utterance.
+template <typename R, int UNITS>
+__global__ void __launch_bounds__(UNITS * kUnitThreads, sizeof(R) == 8 ? (UNITS == 16 ? 1 : 2) : (UNITS == 16 ? 2 : 3))
 k_fe_pass_a(const float* __restrict__ wav, Ragged rg, FeTables tb, FeParams prm, UttStat* __restrict__ stat,
             float* __restrict__ pdb_out, float* __restrict__ mel_raw) {
+    using SM = FeSmemA<R, UNITS>;
+    constexpr int F = SM::F, SPAN = SM::SPAN, THREADS = SM::THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    FeSmemA<R>& sm = *reinterpret_cast<FeSmemA<R>*>(smem_raw);
-    float* mel_db = reinterpret_cast<float*>(smem_raw + sizeof(FeSmemA<R>));
+    SM& sm = *reinterpret_cast<SM*>(smem_raw);
+    float* mel_db = reinterpret_cast<float*>(smem_raw + sizeof(SM));
     constexpr bool kF64 = sizeof(R) == 8;
     const int tid = threadIdx.x;
-    const int tile = blockIdx.x;
-    const int u = find_utt(rg.tile_prefix, rg.n_utts, tile);
-    const int t0 = (tile - rg.tile_prefix[u]) * kFeFrames;
+    const int u = find_utt(rg.tile_prefix, rg.n_utts, blockIdx.x);
+    int k = blockIdx.x - rg.tile_prefix[u];
+    if (rg.int_first != nullptr && k >= rg.int_first[u]) k += rg.int_count[u];   // skip the interior tiles
+    const int t0 = k * F;
     const int T = rg.frame_cnt[u];
-    const int nfr = min(kFeFrames, T - t0);
+    const int nfr = min(F, T - t0);
     const int64_t L = rg.sample_len[u];
     const float* __restrict__ y = wav + rg.sample_off[u];
     const float gain = stat[u].gain;
@@ -279,16 +287,15 @@ k_fe_pass_a(const float* __restrict__ wav, Ragged rg, FeTables tb, FeParams prm,
     {
         const int64_t q0 = (int64_t)t0 * kHop - kNfft / 2;
         const double c = prm.pre_emphasis;
-        if (q0 >= 1 && q0 + kFeSpan <= L) {
-            // interior tile: no reflection, no 64-bit modulo (it costs ~150 instructions per sample)
+        if (q0 >= 1 && q0 + SPAN <= L) {
             const float* __restrict__ src = y + q0;
-            for (int i = tid; i < kFeSpan; i += kFeThreads) {
+            for (int i = tid; i < SPAN; i += THREADS) {
                 const float cur = gain * __ldg(src + i);
                 const float prev = gain * __ldg(src + i - 1);
                 sm.span[i] = (R)((double)cur - c * (double)prev);
             }
         } else {
-            for (int i = tid; i < kFeSpan; i += kFeThreads) {
+            for (int i = tid; i < SPAN; i += THREADS) {
                 const int64_t r = reflect_idx(q0 + i, L);
                 const float cur = gain * __ldg(y + r);
                 const float prev = r > 0 ? gain * __ldg(y + r - 1) : 0.0f;
@@ -296,15 +303,15 @@ k_fe_pass_a(const float* __restrict__ wav, Ragged rg, FeTables tb, FeParams prm,
             }
         }
         if (kF64) {
-            for (int i = tid; i < kNfft; i += kFeThreads) {
+            for (int i = tid; i < kNfft; i += THREADS) {
                 sm.win[i] = (R)tb.win_half_d[i];
                 sm.w400[i] = mk<R>((R)tb.w400_d[i].x, (R)tb.w400_d[i].y);
             }
         } else {
-            for (int i = tid; i < kNfft; i += kFeThreads) sm.win[i] = (R)tb.win_half[i];
+            for (int i = tid; i < kNfft; i += THREADS) sm.win[i] = (R)tb.win_half[i];
         }
-        for (int i = tid; i < kBins; i += kFeThreads) sm.mel_w[i] = tb.mel_w[i];
-        for (int i = tid; i < n_mels + 2; i += kFeThreads) sm.mel_istart[i] = tb.mel_istart[i];
+        for (int i = tid; i < kBins; i += THREADS) sm.mel_w[i] = tb.mel_w[i];
+        for (int i = tid; i < n_mels + 2; i += THREADS) sm.mel_istart[i] = tb.mel_istart[i];
     }
     const int unit = tid / kUnitThreads;
     const int j = tid - unit * kUnitThreads;
@@ -338,9 +345,149 @@ k_fe_pass_a(const float* __restrict__ wav, Ragged rg, FeTables tb, FeParams prm,
     }
     __syncthreads();
 
-    fe_epilogue_a<kFeThreads>(sm.power, kFeFrames, kBins, nfr, sm.mel_w, sm.mel_istart, tb, mel_db, sm.red,
-                              stat + u, pdb_out + (rg.frame_off[u] + t0) * kBins,
-                              mel_raw + (rg.frame_off[u] + t0) * n_mels);
+    fe_epilogue_a<THREADS>(sm.power, F, kBins, nfr, sm.mel_w, sm.mel_istart, tb, mel_db, sm.red,
+                           stat + u, pdb_out + (rg.frame_off[u] + t0) * kBins,
+                           mel_raw + (rg.frame_off[u] + t0) * n_mels);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent, warp-specialised pass A for INTERIOR tiles (no reflect padding needed).
+//   warps 0 .. UNITS*20/32-1 : UNITS units x 20 threads compute tile i
+//   last warp (producer)      : finds tile i+1, writes its descriptor and streams its raw samples
+//                               into the other half of a double buffer with cp.async (LDGSTS)
+// One full-CTA barrier per tile hands a buffer over; the compute warps synchronise among
+// themselves with a named barrier, so the producer's global-load latency never stalls them.
+// Gain and pre-emphasis are applied on the fly when a unit picks its 24 strided samples.
+struct TileDescA {
+    int64_t frame_row;      // first output row of the tile
+    int32_t u, t0, valid;
+    float gain;
+};
+
+template <typename R, int UNITS>
+struct FeSmemP {
+    static constexpr int F = 2 * UNITS;
+    static constexpr int SPAN = kHop * (F - 1) + kNfft;
+    static constexpr int RAW = SPAN + 4;                 // raw[i + 4] = y[q0 + i]; 16-byte aligned start
+    static constexpr int CTHREADS = UNITS * kUnitThreads;
+    R win[kNfft];
+    cx<R> slots[UNITS * kUnitSlots];
+    cx<R> w400[sizeof(R) == 8 ? kNfft : 1];
+    alignas(16) float raw[2][RAW];                       // cp.async 16-byte destinations
+    float power[F * kBins];
+    float2 mel_w[kBins];
+    int32_t mel_istart[kMaxMels + 2];
+    float red[4][(CTHREADS + 31) / 32];
+    TileDescA desc[2];
+    // followed by mel_db[F][n_mels + 1]
+};
+
+template <typename R, int UNITS>
+__global__ void __launch_bounds__(UNITS * kUnitThreads + 32, sizeof(R) == 8 ? 2 : 3)
+k_fe_pass_a_persist(const float* __restrict__ wav, Ragged rg, int total_tiles, FeTables tb, FeParams prm,
+                    UttStat* __restrict__ stat, float* __restrict__ pdb_out, float* __restrict__ mel_raw) {
+    using SM = FeSmemP<R, UNITS>;
+    constexpr int F = SM::F, RAW = SM::RAW, CT = SM::CTHREADS, ALL = CT + 32;
+    static_assert(CT % 32 == 0, "compute threads must fill whole warps");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SM& sm = *reinterpret_cast<SM*>(smem_raw);
+    float* mel_db = reinterpret_cast<float*>(smem_raw + sizeof(SM));
+    constexpr bool kF64 = sizeof(R) == 8;
+    const int tid = threadIdx.x;
+    const int n_mels = tb.n_mels;
+
+    if (tid >= CT) {
+        // ================================ producer warp ================================
+        const int lane = tid - CT;
+        auto produce = [&](int tile, int b) {
+            TileDescA d;
+            d.valid = tile < total_tiles;
+            d.u = 0; d.t0 = 0; d.gain = 0.f; d.frame_row = 0;
+            if (d.valid) {
+                const int u = find_utt(rg.tile_prefix, rg.n_utts, tile);
+                const int k = rg.int_first[u] + (tile - rg.tile_prefix[u]);
+                d.u = u; d.t0 = k * F;
+                d.gain = stat[u].gain;
+                d.frame_row = rg.frame_off[u] + d.t0;
+                const float* __restrict__ src = wav + rg.sample_off[u] + ((int64_t)d.t0 * kHop - kNfft / 2 - 4);
+                float* dst = sm.raw[b];
+                if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+                    for (int i = lane; i < RAW / 4; i += 32) cp_async16(dst + 4 * i, src + 4 * i);
+                } else {
+                    for (int i = lane; i < RAW; i += 32) cp_async4(dst + i, src + i);
+                }
+            }
+            if (lane == 0) sm.desc[b] = d;
+            cp_async_wait_all();
+            return d.valid;
+        };
+        int tile = blockIdx.x, b = 0;
+        produce(tile, 0);
+        bar_sync<0, ALL>();
+        if (tile >= total_tiles) return;
+        while (true) {
+            tile += gridDim.x;
+            const int ok = produce(tile, b ^ 1);
+            bar_sync<0, ALL>();
+            if (!ok) return;
+            b ^= 1;
+        }
+    }
+
+    // ================================== compute warps ==================================
+    if (kF64) {
+        for (int i = tid; i < kNfft; i += CT) {
+            sm.win[i] = (R)tb.win_half_d[i];
+            sm.w400[i] = mk<R>((R)tb.w400_d[i].x, (R)tb.w400_d[i].y);
+        }
+    } else {
+        for (int i = tid; i < kNfft; i += CT) sm.win[i] = (R)tb.win_half[i];
+    }
+    for (int i = tid; i < kBins; i += CT) sm.mel_w[i] = tb.mel_w[i];
+    for (int i = tid; i < n_mels + 2; i += CT) sm.mel_istart[i] = tb.mel_istart[i];
+    const int unit = tid / kUnitThreads;
+    const int j = tid - unit * kUnitThreads;
+    typename FeTw<R>::type tw;
+    if (kF64) tw.load(reinterpret_cast<const cx<R>*>(sm.w400), j);
+    else tw.load(reinterpret_cast<const cx<R>*>(tb.w400), j);
+    cx<R>* unit_slots = sm.slots + unit * kUnitSlots;
+    const double c = prm.pre_emphasis;
+    int b = 0;
+    bar_sync<0, ALL>();
+    while (true) {
+        const TileDescA d = sm.desc[b];
+        if (!d.valid) break;
+        // ---- step 1 with gain (float32) + pre-emphasis (float64) applied on the fly
+        {
+            const float* __restrict__ src = sm.raw[b] + 4 + unit * (2 * kHop) + j;
+            R s[24];
+#pragma unroll
+            for (int m = 0; m < 24; ++m) {
+                const float cur = d.gain * src[20 * m];
+                const float prev = d.gain * src[20 * m - 1];
+                s[m] = (R)((double)cur - c * (double)prev);
+            }
+            cx<R> z[20];
+#pragma unroll
+            for (int n1 = 0; n1 < 20; ++n1) {
+                const R w = sm.win[20 * n1 + j];
+                z[n1] = mk<R>(s[n1] * w, s[n1 + 4] * w);
+            }
+            fwd_step1(z, tw, unit_slots + j);
+        }
+        bar_sync<1, CT>();
+        {
+            cx<R> v[20];
+            fwd_step2(v, unit_slots + j * kSlotLd);
+            float* pa = sm.power + (2 * unit) * kBins;
+            store_power(v, j, pa, pa + kBins);
+        }
+        bar_sync<1, CT>();
+        fe_epilogue_a<CT, 1>(sm.power, F, kBins, F, sm.mel_w, sm.mel_istart, tb, mel_db, sm.red, stat + d.u,
+                             pdb_out + d.frame_row * kBins, mel_raw + d.frame_row * n_mels);
+        bar_sync<0, ALL>();
+        b ^= 1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -373,10 +373,11 @@ extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* s
     cudaStream_t st = (cudaStream_t)stream;
     const int hop = pl->prm.hop_length;
     std::vector<int64_t> slen(n), so(soff, soff + n), fo(foff, foff + n);
-    std::vector<int32_t> fcnt(n), pre_abs(n + 1), pre_a(n + 1), pre_b(n + 1);
+    std::vector<int32_t> fcnt(n), pre_abs(n + 1), pre_a(n + 1), pre_b(n + 1), pre_int(n + 1), ifirst(n), icount(n);
     std::vector<int64_t> heap_off(n + 1);
     int64_t total_frames_span = 0;
-    const int a_frames = pl->fast ? kFeFrames : kGenFeFrames;
+    constexpr int kPU = 8;                         // units per CTA of the fast pass-A kernels (16 frames per tile)
+    const int a_frames = pl->fast ? 2 * kPU : kGenFeFrames;
     for (int u = 0; u < n; ++u) {
         slen[u] = slen_in ? slen_in[u] : soff[u + 1] - soff[u];
         if (slen[u] < 1) return fail(SC_ERR_INVALID, "sc_frontend_batch: empty utterance");
@@ -387,12 +388,23 @@ extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* s
         fcnt[u] = (int32_t)T;
         if (fo[u] + T > total_frames_span) total_frames_span = fo[u] + T;
     }
-    pre_abs[0] = pre_a[0] = pre_b[0] = 0;
+    pre_abs[0] = pre_a[0] = pre_b[0] = pre_int[0] = 0;
     heap_off[0] = 0;
     for (int u = 0; u < n; ++u) {
         const int64_t ta = pre_abs[u] + (int64_t(1) << abs_depth(slen[u]));
         heap_off[u + 1] = heap_off[u] + (int64_t(2) << abs_depth(slen[u]));
-        const int64_t tb = pre_a[u] + (fcnt[u] + a_frames - 1) / a_frames;
+        // interior tiles of the fast path: raw samples [80*t0 - 204, 80*t0 - 200 + SPAN) lie inside the utterance
+        int64_t n_tiles_u = (fcnt[u] + a_frames - 1) / a_frames, k_lo = 0, k_hi = -1;
+        if (pl->fast) {
+            const int64_t span = (int64_t)kHop * (a_frames - 1) + kNfft, step = (int64_t)kHop * a_frames;
+            k_lo = (204 + step - 1) / step;                                  // first k with step*k - 204 >= 0
+            k_hi = slen[u] + 200 - span >= 0 ? (slen[u] + 200 - span) / step : -1;   // last k with step*k - 200 + span <= L
+            if (k_hi > n_tiles_u - 1) k_hi = n_tiles_u - 1;
+        }
+        const int64_t n_int = k_hi >= k_lo ? k_hi - k_lo + 1 : 0;
+        ifirst[u] = (int32_t)k_lo; icount[u] = (int32_t)n_int;
+        pre_int[u + 1] = (int32_t)(pre_int[u] + n_int);
+        const int64_t tb = pre_a[u] + n_tiles_u - n_int;                      // edge (or all generic-path) tiles
         const int64_t tc = pre_b[u] + (fcnt[u] + kFbFrames - 1) / kFbFrames;
         if (ta > INT32_MAX || tb > INT32_MAX) return fail(SC_ERR_INVALID, "sc_frontend_batch: batch too large");
         pre_abs[u + 1] = (int32_t)ta; pre_a[u + 1] = (int32_t)tb; pre_b[u + 1] = (int32_t)tc;
@@ -400,6 +412,7 @@ extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* s
     Blob b;
     const size_t o_so = b.add(so), o_sl = b.add(slen), o_fo = b.add(fo), o_fc = b.add(fcnt);
     const size_t o_pabs = b.add(pre_abs), o_pa = b.add(pre_a), o_pb = b.add(pre_b), o_heap = b.add(heap_off);
+    const size_t o_pint = b.add(pre_int), o_if = b.add(ifirst), o_ic = b.add(icount);
     if (int rc = upload_blob(pl, b, st)) return rc;
 
     // workspace: stats | abs partials | raw mel
@@ -417,6 +430,7 @@ extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* s
     rg.sample_off = at<int64_t>(pl, o_so); rg.sample_len = at<int64_t>(pl, o_sl);
     rg.frame_off = at<int64_t>(pl, o_fo); rg.frame_cnt = at<int32_t>(pl, o_fc);
     rg.n_utts = n;
+    rg.int_first = nullptr; rg.int_count = nullptr;
     const FeTables tb = fe_tables(pl);
     const FeParams fp = fe_params(pl);
 
@@ -434,17 +448,40 @@ extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* s
     rg.tile_prefix = at<int32_t>(pl, o_pa);
     if (pl->fast) {
         static bool attr_set = false;
+        static int n_sm = 0;
         if (!attr_set) {
-            SC_CUDA(cudaFuncSetAttribute(k_fe_pass_a<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-            SC_CUDA(cudaFuncSetAttribute(k_fe_pass_a<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            SC_CUDA(cudaFuncSetAttribute(k_fe_pass_a<float, kPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            SC_CUDA(cudaFuncSetAttribute(k_fe_pass_a<double, kPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+            SC_CUDA(cudaFuncSetAttribute(k_fe_pass_a_persist<float, kPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            SC_CUDA(cudaFuncSetAttribute(k_fe_pass_a_persist<double, kPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+            SC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, pl->device));
             attr_set = true;
         }
-        const size_t mel_bytes = sizeof(float) * kFeFrames * (pl->prm.n_mels + 1);
-        if (pl->fp32_fft)
-            k_fe_pass_a<float><<<pre_a[n], kFeThreads, sizeof(FeSmemA<float>) + mel_bytes, st>>>(wav, rg, tb, fp, stat, pdb, mel_raw);
-        else
-            k_fe_pass_a<double><<<pre_a[n], kFeThreads, sizeof(FeSmemA<double>) + mel_bytes, st>>>(wav, rg, tb, fp, stat, pdb, mel_raw);
-        SC_LAUNCHED();
+        const size_t mel_bytes = sizeof(float) * 2 * kPU * (pl->prm.n_mels + 1);
+        rg.int_first = at<int32_t>(pl, o_if); rg.int_count = at<int32_t>(pl, o_ic);
+        // interior tiles: persistent, warp-specialised, cp.async double-buffered
+        if (pre_int[n] > 0) {
+            rg.tile_prefix = at<int32_t>(pl, o_pint);
+            const int per_sm = pl->fp32_fft ? 3 : 2;
+            const int grid = pre_int[n] < n_sm * per_sm ? pre_int[n] : n_sm * per_sm;
+            if (pl->fp32_fft)
+                k_fe_pass_a_persist<float, kPU><<<grid, kPU * kUnitThreads + 32, sizeof(FeSmemP<float, kPU>) + mel_bytes, st>>>(
+                    wav, rg, pre_int[n], tb, fp, stat, pdb, mel_raw);
+            else
+                k_fe_pass_a_persist<double, kPU><<<grid, kPU * kUnitThreads + 32, sizeof(FeSmemP<double, kPU>) + mel_bytes, st>>>(
+                    wav, rg, pre_int[n], tb, fp, stat, pdb, mel_raw);
+            SC_LAUNCHED();
+        }
+        // edge tiles (reflect padding at the ends of every utterance): one tile per CTA
+        if (pre_a[n] > 0) {
+            rg.tile_prefix = at<int32_t>(pl, o_pa);
+            if (pl->fp32_fft)
+                k_fe_pass_a<float, kPU><<<pre_a[n], kPU * kUnitThreads, sizeof(FeSmemA<float, kPU>) + mel_bytes, st>>>(wav, rg, tb, fp, stat, pdb, mel_raw);
+            else
+                k_fe_pass_a<double, kPU><<<pre_a[n], kPU * kUnitThreads, sizeof(FeSmemA<double, kPU>) + mel_bytes, st>>>(wav, rg, tb, fp, stat, pdb, mel_raw);
+            SC_LAUNCHED();
+        }
+        rg.int_first = nullptr; rg.int_count = nullptr;
     } else {
         GenTables gt{pl->g_fe_win, pl->g_wn_d, pl->prm.n_fft, pl->n_bins, pl->prm.hop_length};
         const size_t smem = gen_fe_smem_bytes(pl->prm.n_fft, pl->prm.hop_length, pl->prm.n_mels);
