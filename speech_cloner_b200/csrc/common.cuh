@@ -45,6 +45,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 template <int ID, int COUNT> __device__ __forceinline__ void bar_sync() {
     if (ID == 0) __syncthreads();
     else asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");

@@ -106,9 +106,14 @@ __global__ void __launch_bounds__(kAbsThreads) k_abs_pairwise(const float* __res
                 res = 0.f;
                 for (int k = 0; k < m; ++k) res += fabsf(__ldg(p + k));
             } else {
-                float r = fabsf(__ldg(p + j));
                 const int body = m - (m % 8);
-                for (int k = 8; k < body; k += 8) r += fabsf(__ldg(p + k + j));
+                float v[16];                              // a leaf has <= 128 samples: <= 16 per lane, all loaded first
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = 8 * q < body ? __ldg(p + 8 * q + j) : 0.f;
+                float r = fabsf(v[0]);
+#pragma unroll
+                for (int q = 1; q < 16; ++q)
+                    if (8 * q < body) r += fabsf(v[q]);
                 r += __shfl_xor_sync(gmask, r, 1, 8);
                 r += __shfl_xor_sync(gmask, r, 2, 8);
                 r += __shfl_xor_sync(gmask, r, 4, 8);
@@ -373,12 +378,12 @@ struct FeSmemP {
     R win[kNfft];
     cx<R> slots[UNITS * kUnitSlots];
     cx<R> w400[sizeof(R) == 8 ? kNfft : 1];
-    alignas(16) float raw[2][RAW];                       // cp.async 16-byte destinations
+    alignas(16) float raw[3][RAW];                       // 3-slot ring of cp.async 16-byte destinations
     float power[F * kBins];
     float2 mel_w[kBins];
     int32_t mel_istart[kMaxMels + 2];
     float red[4][(CTHREADS + 31) / 32];
-    TileDescA desc[2];
+    TileDescA desc[3];
     // followed by mel_db[F][n_mels + 1]
 };
 
@@ -399,7 +404,8 @@ k_fe_pass_a_persist(const float* __restrict__ wav, Ragged rg, int total_tiles, F
     if (tid >= CT) {
         // ================================ producer warp ================================
         const int lane = tid - CT;
-        auto produce = [&](int tile, int b) {
+        // issue(): descriptor + asynchronous copy of one tile's raw samples into ring slot b (one commit group)
+        auto issue = [&](int tile, int b) -> int {
             TileDescA d;
             d.valid = tile < total_tiles;
             d.u = 0; d.t0 = 0; d.gain = 0.f; d.frame_row = 0;
@@ -417,21 +423,28 @@ k_fe_pass_a_persist(const float* __restrict__ wav, Ragged rg, int total_tiles, F
                     for (int i = lane; i < RAW; i += 32) cp_async4(dst + i, src + i);
                 }
             }
+            cp_async_commit();
             if (lane == 0) sm.desc[b] = d;
-            cp_async_wait_all();
             return d.valid;
         };
-        int tile = blockIdx.x, b = 0;
-        produce(tile, 0);
-        bar_sync<0, ALL>();
-        if (tile >= total_tiles) return;
-        while (true) {
-            tile += gridDim.x;
-            const int ok = produce(tile, b ^ 1);
-            bar_sync<0, ALL>();
-            if (!ok) return;
-            b ^= 1;
+        // two tiles in flight: while the compute warps work on tile i, tile i+1 has landed (or is
+        // landing) and tile i+2 is being requested, so one tile period hides the whole
+        // search -> descriptor -> DRAM latency chain
+        const int G = gridDim.x;
+        int tile = blockIdx.x;
+        int ok_cur = issue(tile, 0);
+        int ok_next = issue(tile + G, 1);
+        cp_async_wait_group<1>();
+        bar_sync<0, ALL>();                       // B_0: tile 0 ready
+        int i = 0;
+        while (ok_cur) {
+            const int ok_n2 = issue(tile + 2 * G, (i + 2) % 3);
+            cp_async_wait_group<1>();             // tile i+1 landed
+            bar_sync<0, ALL>();                   // B_{i+1}
+            ok_cur = ok_next; ok_next = ok_n2;
+            tile += G; ++i;
         }
+        return;
     }
 
     // ================================== compute warps ==================================
@@ -486,7 +499,7 @@ k_fe_pass_a_persist(const float* __restrict__ wav, Ragged rg, int total_tiles, F
         fe_epilogue_a<CT, 1>(sm.power, F, kBins, F, sm.mel_w, sm.mel_istart, tb, mel_db, sm.red, stat + d.u,
                              pdb_out + d.frame_row * kBins, mel_raw + d.frame_row * n_mels);
         bar_sync<0, ALL>();
-        b ^= 1;
+        b = b == 2 ? 0 : b + 1;
     }
 }
 
@@ -557,14 +570,21 @@ k_fe_pass_b(Ragged rg, FeTables tb, FeParams prm, const UttStat* __restrict__ st
         if ((base & 3) == 0) {
             float4* __restrict__ p4 = reinterpret_cast<float4*>(p);
             const int n4 = n >> 2;
-            for (int e = tid; e < n4; e += kFbThreads) {
-                float4 v = p4[e];
+            auto fix = [&](float4 v) {
                 v.x = fminf(fmaxf(mul * (fmaxf(v.x, floor_db) - sub), -cl), cl);
                 v.y = fminf(fmaxf(mul * (fmaxf(v.y, floor_db) - sub), -cl), cl);
                 v.z = fminf(fmaxf(mul * (fmaxf(v.z, floor_db) - sub), -cl), cl);
                 v.w = fminf(fmaxf(mul * (fmaxf(v.w, floor_db) - sub), -cl), cl);
-                p4[e] = v;
+                return v;
+            };
+            // 4 independent 16-byte loads in flight per thread (the pass is latency-, not compute-bound)
+            int e = tid;
+            for (; e + 3 * kFbThreads < n4; e += 4 * kFbThreads) {
+                const float4 v0 = p4[e], v1 = p4[e + kFbThreads], v2 = p4[e + 2 * kFbThreads], v3 = p4[e + 3 * kFbThreads];
+                p4[e] = fix(v0); p4[e + kFbThreads] = fix(v1);
+                p4[e + 2 * kFbThreads] = fix(v2); p4[e + 3 * kFbThreads] = fix(v3);
             }
+            for (; e < n4; e += kFbThreads) p4[e] = fix(p4[e]);
             head = n4 << 2;
         }
         for (int e = head + tid; e < n; e += kFbThreads)
@@ -582,21 +602,30 @@ k_fe_pass_b(Ragged rg, FeTables tb, FeParams prm, const UttStat* __restrict__ st
         const float mul = prm.shift_m ? prm.m_db_norm_factor : 1.0f;
         const float cl = prm.clip ? 1.0f : __int_as_float(0x7f800000);
         const int pairs = n_mels / 2;
-        for (int r = warp; r < nfr + 2; r += kWarps) {
-            const int t = t0 - 1 + r;
-            const bool ok = t >= 0 && t < T;
-            const bool own = r >= 1 && r <= nfr;
+        // lanes walk the first half of a row; each warp keeps the loads of 4 rows in flight
+        for (int r0 = warp * 4; r0 < nfr + 2; r0 += kWarps * 4) {
             for (int n = lane; n < L.half; n += 32) {
-                float a = 0.f, b = 0.f;
-                if (ok) {
-                    a = fmaxf(__ldg(src + (int64_t)t * n_mels + n), m_floor);
-                    if (n < pairs) b = fmaxf(__ldg(src + (int64_t)t * n_mels + (n_mels - 1 - n)), m_floor);
-                    if (own) {
-                        dst[(int64_t)t * n_mels + n] = fminf(fmaxf(mul * (a - sub), -cl), cl);
-                        if (n < pairs) dst[(int64_t)t * n_mels + (n_mels - 1 - n)] = fminf(fmaxf(mul * (b - sub), -cl), cl);
-                    }
+                float a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int t = t0 - 1 + r0 + i;
+                    const bool ok = r0 + i < nfr + 2 && t >= 0 && t < T;
+                    a[i] = ok ? __ldg(src + (int64_t)t * n_mels + n) : -1e30f;
+                    b[i] = (ok && n < pairs) ? __ldg(src + (int64_t)t * n_mels + (n_mels - 1 - n)) : -1e30f;
                 }
-                sd_s[r * L.sd_ld + n] = n < pairs ? make_float2(a + b, a - b) : make_float2(a, 0.f);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = r0 + i, t = t0 - 1 + r;
+                    if (r >= nfr + 2) break;
+                    const bool ok = t >= 0 && t < T;
+                    const float x1 = ok ? fmaxf(a[i], m_floor) : 0.f;
+                    const float x2 = (ok && n < pairs) ? fmaxf(b[i], m_floor) : 0.f;
+                    if (ok && r >= 1 && r <= nfr) {
+                        dst[(int64_t)t * n_mels + n] = fminf(fmaxf(mul * (x1 - sub), -cl), cl);
+                        if (n < pairs) dst[(int64_t)t * n_mels + (n_mels - 1 - n)] = fminf(fmaxf(mul * (x2 - sub), -cl), cl);
+                    }
+                    sd_s[r * L.sd_ld + n] = n < pairs ? make_float2(x1 + x2, x1 - x2) : make_float2(x1, 0.f);
+                }
             }
         }
         for (int e = tid; e < L.half * L.ne_pad; e += kFbThreads) { dct_e[e] = tb.dct_e[e]; dct_o[e] = tb.dct_o[e]; }
