@@ -34,6 +34,7 @@ import time
 # the CPU legs count cores explicitly: one BLAS/OpenMP thread per process (set before numpy loads)
 for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
     os.environ.setdefault(_k, "1")
+os.environ["NCCL_DEBUG"] = "WARN"     # stdout carries exactly one JSON line (no NCCL version banner)
 
 import numpy as np  # noqa: E402
 
