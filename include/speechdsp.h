@@ -144,7 +144,8 @@ int sc_griffinlim_chunk_step(sc_plan* plan, const float* amp_dev, const float* p
 /* Per-kernel device timing for the roofline report (bench.py).  When enabled, the next
  * sc_frontend_batch / sc_griffinlim_batch records CUDA events between its kernels on the caller's
  * stream; sc_profile_read waits for them and returns milliseconds:
- *   after sc_frontend_batch:   ms[0] gain (|y| mean), ms[1] pass A (STFT..mel), ms[2] pass B, ms[3] = 0
+ *   after sc_frontend_batch:   ms[0] gain (|y| mean), ms[1] pass A (STFT..mel), ms[2] pass B (summed over the
+ *                              L2-resident utterance groups), ms[3] = number of groups
  *   after sc_griffinlim_batch: ms[0] initial inverse STFT, ms[1] the n_iters-1 iterations, ms[2] 0, ms[3] = n_iters */
 int sc_profile_enable(sc_plan* plan, int32_t on);
 int sc_profile_read(sc_plan* plan, double* ms_out4);

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -116,9 +117,11 @@ struct sc_plan {
     DevBuf work, work2;
     // optional per-kernel timing (bench.py's roofline): events recorded on the caller's stream
     bool profile = false;
-    cudaEvent_t pev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> pev;   // 4 events per front-end group, or 3 for a Griffin-Lim call
+    int pev_groups = 0;
     int pev_kind = 0;        // 1 = front-end (gain | pass A | pass B), 2 = Griffin-Lim (init | iterations)
     int pev_iters = 0;
+    int64_t fe_group_frames = int64_t(1) << 60;   // frames per front-end group (env SC_FE_GROUP_FRAMES); measured: grouping for L2 residency only adds launch latency, so off by default
 };
 
 static int upload_blob(DescStage& ds, const Blob& b, cudaStream_t st) {
@@ -255,6 +258,7 @@ extern "C" int sc_plan_create(const sc_params* p, sc_plan** out) {
     pl->n_bins = 1 + p->n_fft / 2;
     pl->fast = (p->n_fft == kNfft && p->hop_length == kHop);
     pl->fp32_fft = p->fft_precision == 1;
+    if (const char* e = getenv("SC_FE_GROUP_FRAMES")) { const long long v = atoll(e); if (v > 0) pl->fe_group_frames = v; }
     cudaGetDevice(&pl->device);
 
     std::vector<double> w = p->window_host ? std::vector<double>(p->window_host, p->window_host + p->win_length)
@@ -340,6 +344,16 @@ extern "C" int sc_plan_is_fast_path(const sc_plan* pl) { return pl && pl->fast ?
 
 extern "C" int64_t sc_num_frames(const sc_plan* pl, int64_t n) { return pl ? 1 + n / pl->prm.hop_length : 0; }
 
+static int prof_event(sc_plan* pl, int idx, cudaStream_t st) {
+    while ((int)pl->pev.size() <= idx) {
+        cudaEvent_t e = nullptr;
+        SC_CUDA(cudaEventCreate(&e));
+        pl->pev.push_back(e);
+    }
+    SC_CUDA(cudaEventRecord(pl->pev[idx], st));
+    return 0;
+}
+
 static FeTables fe_tables(const sc_plan* pl) {
     FeTables t;
     t.w400 = pl->w400; t.win_half = pl->fe_win_half; t.w400_d = pl->w400_d; t.win_half_d = pl->fe_win_half_d;
@@ -366,25 +380,18 @@ static FeParams fe_params(const sc_plan* pl) {
 }
 
 // ------------------------------------------------------------------------------ front-end
-extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* soff, const int64_t* slen_in,
-                                 int32_t n, float* mfcc, float* mel, float* pdb, const int64_t* foff, void* stream) {
-    if (!pl || !wav || !soff || !mfcc || !mel || !pdb || !foff) return fail(SC_ERR_INVALID, "sc_frontend_batch: null argument");
-    if (n <= 0) return SC_OK;
-    cudaStream_t st = (cudaStream_t)stream;
+// one L2-resident group of utterances [0, n) (pointers already offset by the caller)
+static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, const int64_t* slen_in, int32_t n,
+                          float* mfcc, float* mel, float* pdb, const int64_t* foff, cudaStream_t st, int group) {
     const int hop = pl->prm.hop_length;
-    std::vector<int64_t> slen(n), so(soff, soff + n), fo(foff, foff + n);
+    std::vector<int64_t> slen(slen_in, slen_in + n), so(soff, soff + n), fo(foff, foff + n);
     std::vector<int32_t> fcnt(n), pre_abs(n + 1), pre_a(n + 1), pre_b(n + 1), pre_int(n + 1), ifirst(n), icount(n);
     std::vector<int64_t> heap_off(n + 1);
     int64_t total_frames_span = 0;
     constexpr int kPU = 8;                         // units per CTA of the fast pass-A kernels (16 frames per tile)
     const int a_frames = pl->fast ? 2 * kPU : kGenFeFrames;
     for (int u = 0; u < n; ++u) {
-        slen[u] = slen_in ? slen_in[u] : soff[u + 1] - soff[u];
-        if (slen[u] < 1) return fail(SC_ERR_INVALID, "sc_frontend_batch: empty utterance");
         const int64_t T = 1 + slen[u] / hop;
-        if (T > INT32_MAX / 4) return fail(SC_ERR_INVALID, "sc_frontend_batch: utterance too long");
-        if (pl->prm.calc_mfcc_derivative && T < 2)
-            return fail(SC_ERR_INVALID, "calc_mfcc_derivate needs at least 2 frames (len >= hop_length)");
         fcnt[u] = (int32_t)T;
         if (fo[u] + T > total_frames_span) total_frames_span = fo[u] + T;
     }
@@ -434,7 +441,7 @@ extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* s
     const FeTables tb = fe_tables(pl);
     const FeParams fp = fe_params(pl);
 
-    if (pl->profile) { SC_CUDA(cudaEventRecord(pl->pev[0], st)); pl->pev_kind = 1; }
+    if (pl->profile) { if (int rc = prof_event(pl, 4 * group, st)) return rc; pl->pev_kind = 1; pl->pev_groups = group + 1; }
     if (fp.use_gain) {
         rg.tile_prefix = at<int32_t>(pl, o_pabs);
         k_abs_pairwise<<<pre_abs[n], kAbsThreads, 0, st>>>(wav, rg, at<int64_t>(pl, o_heap), heap);
@@ -444,7 +451,7 @@ extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* s
     k_gain_finalize<<<(n + 3) / 4, 128, 0, st>>>(rg, at<int64_t>(pl, o_heap), heap, stat, fp.mean_abs_amp_norm, fp.use_gain, nullptr);
     SC_LAUNCHED();
 
-    if (pl->profile) SC_CUDA(cudaEventRecord(pl->pev[1], st));
+    if (pl->profile) if (int rc = prof_event(pl, 4 * group + 1, st)) return rc;
     rg.tile_prefix = at<int32_t>(pl, o_pa);
     if (pl->fast) {
         static bool attr_set = false;
@@ -489,7 +496,7 @@ extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* s
         k_gen_fe_pass_a<<<pre_a[n], kGenThreads, smem, st>>>(wav, rg, gt, tb, fp, stat, pdb, mel_raw);
         SC_LAUNCHED();
     }
-    if (pl->profile) SC_CUDA(cudaEventRecord(pl->pev[2], st));
+    if (pl->profile) if (int rc = prof_event(pl, 4 * group + 2, st)) return rc;
     rg.tile_prefix = at<int32_t>(pl, o_pb);
     {
         const size_t smem = fb_layout(pl->prm.n_mels, pl->prm.n_mfcc).bytes;
@@ -497,7 +504,46 @@ extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* s
         k_fe_pass_b<<<pre_b[n], kFbThreads, smem, st>>>(rg, tb, fp, stat, mel_raw, pdb, mel, mfcc, pl->n_bins);
         SC_LAUNCHED();
     }
-    if (pl->profile) SC_CUDA(cudaEventRecord(pl->pev[3], st));
+    if (pl->profile) if (int rc = prof_event(pl, 4 * group + 3, st)) return rc;
+    return SC_OK;
+}
+
+extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* soff, const int64_t* slen_in,
+                                 int32_t n, float* mfcc, float* mel, float* pdb, const int64_t* foff, void* stream) {
+    if (!pl || !wav || !soff || !mfcc || !mel || !pdb || !foff) return fail(SC_ERR_INVALID, "sc_frontend_batch: null argument");
+    if (n <= 0) return SC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int hop = pl->prm.hop_length;
+    std::vector<int64_t> slen(n);
+    int64_t max_row = 0, heap_total = 0;
+    for (int u = 0; u < n; ++u) {
+        slen[u] = slen_in ? slen_in[u] : soff[u + 1] - soff[u];
+        if (slen[u] < 1) return fail(SC_ERR_INVALID, "sc_frontend_batch: empty utterance");
+        const int64_t T = 1 + slen[u] / hop;
+        if (T > INT32_MAX / 4) return fail(SC_ERR_INVALID, "sc_frontend_batch: utterance too long");
+        if (pl->prm.calc_mfcc_derivative && T < 2)
+            return fail(SC_ERR_INVALID, "calc_mfcc_derivate needs at least 2 frames (len >= hop_length)");
+        if (foff[u] + T > max_row) max_row = foff[u] + T;
+        heap_total += int64_t(2) << abs_depth(slen[u]);
+    }
+    // one allocation that fits every group (frontend_range never has to grow it mid-batch)
+    const size_t bound = ((sizeof(UttStat) * n + 255) & ~size_t(255)) + ((sizeof(float) * (size_t)heap_total + 255) & ~size_t(255)) +
+                         256 + sizeof(float) * (size_t)max_row * pl->prm.n_mels;
+    if (int rc = pl->work.ensure(bound)) return rc;
+    // Groups of consecutive utterances whose raw dB intermediates (1 124 B/frame) stay L2-resident between
+    // pass A and pass B: pass B then re-reads from L2 and the raw values are overwritten before they reach DRAM.
+    int group = 0;
+    for (int u0 = 0; u0 < n;) {
+        int u1 = u0;
+        int64_t frames = 0;
+        while (u1 < n && (u1 == u0 || frames + 1 + slen[u1] / hop <= pl->fe_group_frames)) {
+            frames += 1 + slen[u1] / hop;
+            ++u1;
+        }
+        if (int rc = frontend_range(pl, wav, soff + u0, slen.data() + u0, u1 - u0, mfcc, mel, pdb, foff + u0, st, group)) return rc;
+        u0 = u1;
+        ++group;
+    }
     return SC_OK;
 }
 
@@ -725,9 +771,9 @@ extern "C" int sc_griffinlim_batch(sc_plan* pl, const float* amp, const float* p
     const int32_t* dp = at<int32_t>(pl, o_p);
     // iteration i writes buffer (n_iters - 1 - i) & 1 ? other : wav, so the last one lands in `wav`
     auto buf = [&](int i) { return ((n_iters - 1 - i) & 1) ? other : wav; };
-    if (pl->profile) { SC_CUDA(cudaEventRecord(pl->pev[0], st)); pl->pev_kind = 2; pl->pev_iters = n_iters; }
+    if (pl->profile) { if (int rc = prof_event(pl, 0, st)) return rc; pl->pev_kind = 2; pl->pev_iters = n_iters; }
     if (int rc = gl_launch(pl, true, dj, n, dp, prefix[n], amp, phase0, nullptr, buf(0), st)) return rc;
-    if (pl->profile) SC_CUDA(cudaEventRecord(pl->pev[1], st));
+    if (pl->profile) if (int rc = prof_event(pl, 1, st)) return rc;
     for (int i = 1; i < n_iters; ++i) {
         if (int rc = gl_launch(pl, false, dj, n, dp, prefix[n], amp, phase0, buf(i - 1), buf(i), st)) return rc;
         if (rms && rprefix[n] > 0) {
@@ -737,7 +783,7 @@ extern "C" int sc_griffinlim_batch(sc_plan* pl, const float* amp, const float* p
             SC_LAUNCHED();
         }
     }
-    if (pl->profile) SC_CUDA(cudaEventRecord(pl->pev[2], st));
+    if (pl->profile) if (int rc = prof_event(pl, 2, st)) return rc;
     return SC_OK;
 }
 
@@ -784,9 +830,6 @@ extern "C" int sc_transpose_to_f32(const void* src, int32_t is_f64, int64_t rows
 
 extern "C" int sc_profile_enable(sc_plan* pl, int32_t on) {
     if (!pl) return fail(SC_ERR_INVALID, "sc_profile_enable: null plan");
-    if (on)
-        for (auto& e : pl->pev)
-            if (!e) SC_CUDA(cudaEventCreate(&e));
     pl->profile = on != 0;
     pl->pev_kind = 0;
     return SC_OK;
@@ -796,14 +839,24 @@ extern "C" int sc_profile_read(sc_plan* pl, double* ms_out) {
     if (!pl || !ms_out) return fail(SC_ERR_INVALID, "sc_profile_read: null argument");
     for (int i = 0; i < 4; ++i) ms_out[i] = 0.0;
     if (!pl->profile || pl->pev_kind == 0) return fail(SC_ERR_INVALID, "sc_profile_read: nothing recorded");
-    const int last = pl->pev_kind == 1 ? 3 : 2;
-    SC_CUDA(cudaEventSynchronize(pl->pev[last]));
-    for (int i = 0; i < last; ++i) {
-        float ms = 0.f;
-        SC_CUDA(cudaEventElapsedTime(&ms, pl->pev[i], pl->pev[i + 1]));
-        ms_out[i] = ms;
+    if (pl->pev_kind == 1) {
+        SC_CUDA(cudaEventSynchronize(pl->pev[4 * (pl->pev_groups - 1) + 3]));
+        for (int g = 0; g < pl->pev_groups; ++g)
+            for (int i = 0; i < 3; ++i) {
+                float ms = 0.f;
+                SC_CUDA(cudaEventElapsedTime(&ms, pl->pev[4 * g + i], pl->pev[4 * g + i + 1]));
+                ms_out[i] += ms;
+            }
+        ms_out[3] = (double)pl->pev_groups;
+    } else {
+        SC_CUDA(cudaEventSynchronize(pl->pev[2]));
+        for (int i = 0; i < 2; ++i) {
+            float ms = 0.f;
+            SC_CUDA(cudaEventElapsedTime(&ms, pl->pev[i], pl->pev[i + 1]));
+            ms_out[i] = ms;
+        }
+        ms_out[3] = (double)pl->pev_iters;
     }
-    ms_out[3] = pl->pev_kind == 2 ? (double)pl->pev_iters : 0.0;
     return SC_OK;
 }
 
