@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--no-gl", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--gl-long", action="store_true", help="also time the chapter-length chunked Griffin-Lim (configs[3])")
+    ap.add_argument("--sweep", action="store_true", help="also time the 10 h featurization sweep (configs[4]), utterance-sharded")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pipeline leg (profiling runs)")
     ap.add_argument("--no-probe", action="store_true", help="skip the 1.2 s clock probe loop (profiling runs)")
     args = ap.parse_args()
@@ -373,6 +374,36 @@ def main():
                            "ms_per_step": long_ms, "value": (80 * (T_long - 1) / SR) / (long_ms * 1e-3), "unit": "audio-s/s",
                            "scaling": "strong"}
 
+    # ---- dataset-scale sweep, configs[4]: 10 h = 6000 x 3 s (TIMIT-shaped, gain 10) + 4500 x 4 s, sharded by frames
+    sweep = None
+    if args.sweep:
+        from speech_cloner_b200 import distributed as D
+        lens = [48000] * 6000 + [64000] * 4500
+        mine = D.shard_by_frames(lens, world, 80)[rank]
+        pool3 = synth.batch(5, 16, 3.0, ds_norm=(0.0, 10.0))
+        pool4 = wavs[:16]
+        slay = al.FrontendLayout([lens[i] for i in mine], 80)
+        sdev = torch.empty(slay.total_samples, dtype=torch.float32, device="cuda")
+        p3 = [torch.from_numpy(w).cuda() for w in pool3]
+        p4 = [torch.from_numpy(w).cuda() for w in pool4]
+        for k, (i, o) in enumerate(zip(mine, slay.sample_offsets)):
+            src = p3[i % 16] if lens[i] == 48000 else p4[i % 16]
+            sdev[o:o + lens[i]] = src                                     # 16 distinct utterances per shape, tiled
+        sout = al.frontend_device(plan, sdev, slay)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            al.frontend_device(plan, sdev, slay, sout)
+        b.record()
+        barrier()
+        sw_ms = max_over_ranks(a.elapsed_time(b) / 3)
+        sweep = {"workload": "configs[4]: 10 h = 6000 x 3 s + 4500 x 4 s, utterances sharded by frame count (LPT) over "
+                             f"{world} rank(s), device resident, 16 distinct synthetic utterances per shape tiled",
+                 "ms_per_pass": sw_ms, "value": 36000.0 / (sw_ms * 1e-3), "unit": "audio-s/s", "scaling": "strong",
+                 "frac_hbm": FE_BYTES_PER_FRAME * (6000 * 601 + 4500 * 801) / world / (sw_ms * 1e-3) / 1e9 / peak}
+        del sdev, sout
+
     clocks = None
     if sampler:
         time.sleep(0.1)
@@ -409,7 +440,7 @@ def main():
                        "l2": "inputs+outputs (361.6 MB) larger than L2, no flush",
                        "parallelism": f"utterance shards, {world} rank(s), no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "griffin_lim": gl,
+            "griffin_lim": gl, "sweep_10h": sweep,
         }
         print(json.dumps(line))
     if world > 1:

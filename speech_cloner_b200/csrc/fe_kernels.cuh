@@ -629,18 +629,22 @@ k_fe_pass_b(Ragged rg, FeTables tb, FeParams prm, const UttStat* __restrict__ st
             }
         }
         for (int e = tid; e < L.half * L.ne_pad; e += kFbThreads) { dct_e[e] = tb.dct_e[e]; dct_o[e] = tb.dct_o[e]; }
-        // MFCC[0, 0] of the utterance (:221): first DCT row applied to frame 0
+        // MFCC[0, 0] of the utterance (:221): first DCT row applied to frame 0, accumulated with exactly the
+        // FMA sequence of the DCT task below, so that MFCC[0, 0] - MFCC[0, 0] is exactly 0 like the reference's
         if (warp == kWarps - 1) {
-            float a = 0.f;
-            if (prm.norm_first)
-                for (int n = lane; n < L.half; n += 32) {
-                    const float x1 = fmaxf(__ldg(src + n), m_floor);
-                    const float x2 = n < pairs ? fmaxf(__ldg(src + (n_mels - 1 - n)), m_floor) : 0.f;
-                    a = fmaf(__ldg(tb.dct_e + n * L.ne_pad), x1 + x2, a);
-                }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (lane == 0) c00_s[0] = a;
+            float* scratch = cc_s;                               // free until the DCT phase
+            for (int n = lane; n < L.half; n += 32) {
+                const float x1 = fmaxf(__ldg(src + n), m_floor);
+                const float x2 = n < pairs ? fmaxf(__ldg(src + (n_mels - 1 - n)), m_floor) : 0.f;
+                scratch[n] = n < pairs ? x1 + x2 : x1;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                float a = 0.f;
+                if (prm.norm_first)
+                    for (int n = 0; n < L.half; ++n) a = fmaf(__ldg(tb.dct_e + n * L.ne_pad), scratch[n], a);
+                c00_s[0] = a;
+            }
         }
     }
     __syncthreads();
