@@ -267,6 +267,26 @@ def main():
         "step_ms_back_to_back": ms_step,
     }
 
+    # ---- opt-in float32-FFT mode of the same step (documented accuracy: < 1e-4 abs, >= 99.7 % inside 1e-4/1e-5)
+    alt = None
+    if args.precision == "fp64":
+        kw32 = dict(plan_kw); kw32["fft_precision"] = "fp32"
+        plan32 = al.DspPlan(**kw32)
+        for _ in range(args.warmup):
+            al.frontend_device(plan32, wav_dev, lay, out)
+        barrier()
+        a32, b32 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a32.record()
+        for _ in range(args.steps):
+            al.frontend_device(plan32, wav_dev, lay, out)
+        b32.record()
+        barrier()
+        ms32 = max_over_ranks(a32.elapsed_time(b32) / args.steps)
+        alt = {"fft_precision": "fp32", "ms_per_step": ms32, "value": world * audio_s / (ms32 * 1e-3), "unit": "audio-s/s",
+               "roofline_frac": fe_bytes / (ms32 * 1e-3) / 1e9 / peak,
+               "note": "not the default: bins 70-80 dB below the utterance maximum can deviate by up to ~5e-5"}
+        del plan32
+
     # ---- clock probe: keep the same step running ~1.2 s so nvidia-smi (50 ms period) sees it under load
     if rank == 0 and not args.no_probe:
         w0 = time.time()
@@ -440,7 +460,7 @@ def main():
                        "l2": "inputs+outputs (361.6 MB) larger than L2, no flush",
                        "parallelism": f"utterance shards, {world} rank(s), no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "griffin_lim": gl, "sweep_10h": sweep,
+            "frontend_fp32_mode": alt, "griffin_lim": gl, "sweep_10h": sweep,
         }
         print(json.dumps(line))
     if world > 1:

@@ -356,7 +356,7 @@ k_fe_pass_a(const float* __restrict__ wav, Ragged rg, FeTables tb, FeParams prm,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Persistent, warp-specialised pass A for INTERIOR tiles (no reflect padding needed).
+// Persistent, warp-specialised pass A (all tiles of utterances at least two tiles long).
 //   warps 0 .. UNITS*20/32-1 : UNITS units x 20 threads compute tile i
 //   last warp (producer)      : finds tile i+1, writes its descriptor and streams its raw samples
 //                               into the other half of a double buffer with cp.async (LDGSTS)
@@ -365,7 +365,11 @@ k_fe_pass_a(const float* __restrict__ wav, Ragged rg, FeTables tb, FeParams prm,
 // Gain and pre-emphasis are applied on the fly when a unit picks its 24 strided samples.
 struct TileDescA {
     int64_t frame_row;      // first output row of the tile
+    int64_t q0;             // utterance sample index of the tile's first (reflect-padded) sample
+    int64_t L;              // utterance length
     int32_t u, t0, valid;
+    int32_t edge;           // the tile touches the reflect padding (first / last tiles of an utterance)
+    int32_t nfr;            // frames of the tile that exist
     float gain;
 };
 
@@ -373,7 +377,7 @@ template <typename R, int UNITS>
 struct FeSmemP {
     static constexpr int F = 2 * UNITS;
     static constexpr int SPAN = kHop * (F - 1) + kNfft;
-    static constexpr int RAW = SPAN + 4;                 // raw[i + 4] = y[q0 + i]; 16-byte aligned start
+    static constexpr int RAW = SPAN + 8;                 // raw[i + 4] = y[reflect(q0 + i)]; 16-byte aligned start, +1 look-ahead
     static constexpr int CTHREADS = UNITS * kUnitThreads;
     R win[kNfft];
     cx<R> slots[UNITS * kUnitSlots];
@@ -408,19 +412,34 @@ k_fe_pass_a_persist(const float* __restrict__ wav, Ragged rg, int total_tiles, F
         auto issue = [&](int tile, int b) -> int {
             TileDescA d;
             d.valid = tile < total_tiles;
-            d.u = 0; d.t0 = 0; d.gain = 0.f; d.frame_row = 0;
+            d.u = 0; d.t0 = 0; d.gain = 0.f; d.frame_row = 0; d.q0 = 0; d.L = 1; d.edge = 0; d.nfr = 0;
             if (d.valid) {
                 const int u = find_utt(rg.tile_prefix, rg.n_utts, tile);
                 const int k = rg.int_first[u] + (tile - rg.tile_prefix[u]);
                 d.u = u; d.t0 = k * F;
+                d.nfr = min(F, rg.frame_cnt[u] - d.t0);
                 d.gain = stat[u].gain;
                 d.frame_row = rg.frame_off[u] + d.t0;
-                const float* __restrict__ src = wav + rg.sample_off[u] + ((int64_t)d.t0 * kHop - kNfft / 2 - 4);
+                d.L = rg.sample_len[u];
+                d.q0 = (int64_t)d.t0 * kHop - kNfft / 2;
+                d.edge = !(d.q0 - 4 >= 0 && d.q0 + SM::SPAN + 4 <= d.L);
+                const float* __restrict__ y = wav + rg.sample_off[u];
                 float* dst = sm.raw[b];
-                if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-                    for (int i = lane; i < RAW / 4; i += 32) cp_async16(dst + 4 * i, src + 4 * i);
+                if (!d.edge) {
+                    const float* __restrict__ src = y + (d.q0 - 4);
+                    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+                        for (int i = lane; i < RAW / 4; i += 32) cp_async16(dst + 4 * i, src + 4 * i);
+                    } else {
+                        for (int i = lane; i < RAW; i += 32) cp_async4(dst + i, src + i);
+                    }
                 } else {
-                    for (int i = lane; i < RAW; i += 32) cp_async4(dst + i, src + i);
+                    // first / last tiles: np.pad(.., 'reflect') (:147) as a gather; the host guarantees a single
+                    // reflection per side (utterances shorter than 2 tiles go to the plain kernel)
+                    for (int i = lane; i < RAW; i += 32) {
+                        const int64_t q = d.q0 - 4 + i;
+                        const int64_t r = q < 0 ? -q : (q > d.L - 1 ? 2 * (d.L - 1) - q : q);
+                        cp_async4(dst + i, y + r);
+                    }
                 }
             }
             cp_async_commit();
@@ -474,11 +493,24 @@ k_fe_pass_a_persist(const float* __restrict__ wav, Ragged rg, int total_tiles, F
         {
             const float* __restrict__ src = sm.raw[b] + 4 + unit * (2 * kHop) + j;
             R s[24];
+            if (!d.edge) {
 #pragma unroll
-            for (int m = 0; m < 24; ++m) {
-                const float cur = d.gain * src[20 * m];
-                const float prev = d.gain * src[20 * m - 1];
-                s[m] = (R)((double)cur - c * (double)prev);
+                for (int m = 0; m < 24; ++m) {
+                    const float cur = d.gain * src[20 * m];
+                    const float prev = d.gain * src[20 * m - 1];
+                    s[m] = (R)((double)cur - c * (double)prev);
+                }
+            } else {
+                // y[r - 1] of a reflected sample is its right-hand neighbour in the padded order; y[-1] = 0 (:27)
+                const int64_t qb = d.q0 + unit * (2 * kHop) + j;
+#pragma unroll
+                for (int m = 0; m < 24; ++m) {
+                    const int64_t q = qb + 20 * m;
+                    const float cur = d.gain * src[20 * m];
+                    const float nb = (q < 0 || q > d.L - 1) ? src[20 * m + 1] : src[20 * m - 1];
+                    const float prev = q == 0 ? 0.0f : d.gain * nb;
+                    s[m] = (R)((double)cur - c * (double)prev);
+                }
             }
             cx<R> z[20];
 #pragma unroll
@@ -496,7 +528,7 @@ k_fe_pass_a_persist(const float* __restrict__ wav, Ragged rg, int total_tiles, F
             store_power(v, j, pa, pa + kBins);
         }
         bar_sync<1, CT>();
-        fe_epilogue_a<CT, 1>(sm.power, F, kBins, F, sm.mel_w, sm.mel_istart, tb, mel_db, sm.red, stat + d.u,
+        fe_epilogue_a<CT, 1>(sm.power, F, kBins, d.nfr, sm.mel_w, sm.mel_istart, tb, mel_db, sm.red, stat + d.u,
                              pdb_out + d.frame_row * kBins, mel_raw + d.frame_row * n_mels);
         bar_sync<0, ALL>();
         b = b == 2 ? 0 : b + 1;

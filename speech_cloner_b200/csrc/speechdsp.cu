@@ -400,13 +400,13 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
     for (int u = 0; u < n; ++u) {
         const int64_t ta = pre_abs[u] + (int64_t(1) << abs_depth(slen[u]));
         heap_off[u + 1] = heap_off[u] + (int64_t(2) << abs_depth(slen[u]));
-        // interior tiles of the fast path: raw samples [80*t0 - 204, 80*t0 - 200 + SPAN) lie inside the utterance
+        // fast path: every tile of an utterance at least two tile spans long runs in the persistent kernel (its
+        // first / last tiles gather their reflect padding); shorter utterances, whose padding could wrap more
+        // than once, use the plain kernel
         int64_t n_tiles_u = (fcnt[u] + a_frames - 1) / a_frames, k_lo = 0, k_hi = -1;
         if (pl->fast) {
-            const int64_t span = (int64_t)kHop * (a_frames - 1) + kNfft, step = (int64_t)kHop * a_frames;
-            k_lo = (204 + step - 1) / step;                                  // first k with step*k - 204 >= 0
-            k_hi = slen[u] + 200 - span >= 0 ? (slen[u] + 200 - span) / step : -1;   // last k with step*k - 200 + span <= L
-            if (k_hi > n_tiles_u - 1) k_hi = n_tiles_u - 1;
+            const int64_t span = (int64_t)kHop * (a_frames - 1) + kNfft;
+            if (slen[u] >= 2 * span + 16) k_hi = n_tiles_u - 1;
         }
         const int64_t n_int = k_hi >= k_lo ? k_hi - k_lo + 1 : 0;
         ifirst[u] = (int32_t)k_lo; icount[u] = (int32_t)n_int;
@@ -466,7 +466,7 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
         }
         const size_t mel_bytes = sizeof(float) * 2 * kPU * (pl->prm.n_mels + 1);
         rg.int_first = at<int32_t>(pl, o_if); rg.int_count = at<int32_t>(pl, o_ic);
-        // interior tiles: persistent, warp-specialised, cp.async double-buffered
+        // persistent, warp-specialised, cp.async ring
         if (pre_int[n] > 0) {
             rg.tile_prefix = at<int32_t>(pl, o_pint);
             const int per_sm = pl->fp32_fft ? 3 : 2;
@@ -479,7 +479,7 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
                     wav, rg, pre_int[n], tb, fp, stat, pdb, mel_raw);
             SC_LAUNCHED();
         }
-        // edge tiles (reflect padding at the ends of every utterance): one tile per CTA
+        // utterances too short for the persistent kernel: one tile per CTA
         if (pre_a[n] > 0) {
             rg.tile_prefix = at<int32_t>(pl, o_pa);
             if (pl->fp32_fft)
