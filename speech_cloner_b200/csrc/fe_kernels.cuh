@@ -341,12 +341,14 @@ k_fe_pass_a(const float* __restrict__ wav, Ragged rg, FeTables tb, FeParams prm,
         fwd_step1(z, tw, unit_slots + j);
     }
     __syncthreads();
-    // ---- step 2 + |X|^2
+    // ---- step 2 + |X|^2 (packed columns on the lowest thread ids, see step2_task)
     {
+        int u2, c2;
+        step2_task(tid, UNITS, u2, c2);
         cx<R> v[20];
-        fwd_step2(v, unit_slots + j * kSlotLd);
-        float* pa = sm.power + (2 * unit) * kBins;
-        store_power(v, j, pa, pa + kBins);
+        fwd_step2(v, sm.slots + u2 * kUnitSlots + c2 * kSlotLd);
+        float* pa = sm.power + (2 * u2) * kBins;
+        store_power(v, c2, pa, pa + kBins);
     }
     __syncthreads();
 
@@ -522,10 +524,12 @@ k_fe_pass_a_persist(const float* __restrict__ wav, Ragged rg, int total_tiles, F
         }
         bar_sync<1, CT>();
         {
+            int u2, c2;
+            step2_task(tid, UNITS, u2, c2);
             cx<R> v[20];
-            fwd_step2(v, unit_slots + j * kSlotLd);
-            float* pa = sm.power + (2 * unit) * kBins;
-            store_power(v, j, pa, pa + kBins);
+            fwd_step2(v, sm.slots + u2 * kUnitSlots + c2 * kSlotLd);
+            float* pa = sm.power + (2 * u2) * kBins;
+            store_power(v, c2, pa, pa + kBins);
         }
         bar_sync<1, CT>();
         fe_epilogue_a<CT, 1>(sm.power, F, kBins, d.nfr, sm.mel_w, sm.mel_istart, tb, mel_db, sm.red, stat + d.u,

@@ -91,6 +91,22 @@ SC_HD void fwd_step2(cx<R> (&v)[20], const cx<R>* __restrict__ slot_row) {
     dft20<false>(v);
 }
 
+// Step-2 work assignment.  A step-2 task is (unit, column c); its inputs come from shared memory, so any
+// thread can run any task.  The packed columns c = 0 and c = 10 take a different code path than the
+// 18 one-frame columns: give them to the lowest thread ids so that only the first warp diverges instead
+// of every warp executing all three paths.
+SC_HD void step2_task(int tid, int units, int& unit, int& c) {
+    if (tid < 2 * units) {
+        unit = tid >> 1;
+        c = (tid & 1) ? 10 : 0;
+    } else {
+        const int g = tid - 2 * units;
+        unit = g / 18;
+        const int r = g - unit * 18;
+        c = r < 9 ? r + 1 : r + 2;
+    }
+}
+
 // bin owned by generic column (k1 in 1..9) at position k2
 SC_HD constexpr int own_bin(int k1, int k2) { return k2 < 10 ? k1 + 20 * k2 : (20 - k1) + 20 * (19 - k2); }
 

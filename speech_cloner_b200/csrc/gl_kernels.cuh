@@ -130,19 +130,26 @@ k_gl_iter(const GlJob* __restrict__ jobs, int n_jobs, const int32_t* __restrict_
         __syncthreads();
     }
     {
-        const int64_t ra = job.amp_row0 + (va ? fa - job.f_lo : 0);
-        const int64_t rb = job.amp_row0 + (vb ? fb - job.f_lo : 0);
-        const float* __restrict__ amp_a = va ? amp + ra * kBins : tb.zero_row;
-        const float* __restrict__ amp_b = vb ? amp + rb * kBins : tb.zero_row;
+        // step-2 task of this thread (packed columns on warp 0, see step2_task) and its unit's two frames
+        int u2, c2;
+        step2_task(tid, kFeUnits, u2, c2);
+        const int ga = t0 + 2 * u2, gb = ga + 1;
+        const bool wa = ga >= job.f_lo && ga < job.f_lo + job.f_cnt && ga < T;
+        const bool wb = gb >= job.f_lo && gb < job.f_lo + job.f_cnt && gb < T;
+        const int64_t ra = job.amp_row0 + (wa ? ga - job.f_lo : 0);
+        const int64_t rb = job.amp_row0 + (wb ? gb - job.f_lo : 0);
+        const float* __restrict__ amp_a = wa ? amp + ra * kBins : tb.zero_row;
+        const float* __restrict__ amp_b = wb ? amp + rb * kBins : tb.zero_row;
+        cxf* row = sm.slots + u2 * kUnitSlots + c2 * kSlotLd;
         cxf v[20];
         if (INIT) {
-            gl_init_state(v, j, amp_a, amp_b, va ? phase0 + ra * kBins : tb.zero_row,
-                          vb ? phase0 + rb * kBins : tb.zero_row);
+            gl_init_state(v, c2, amp_a, amp_b, wa ? phase0 + ra * kBins : tb.zero_row,
+                          wb ? phase0 + rb * kBins : tb.zero_row);
         } else {
-            fwd_step2(v, unit_slots + j * kSlotLd);
-            gl_update(v, j, amp_a, amp_b);
+            fwd_step2(v, row);
+            gl_update(v, c2, amp_a, amp_b);
         }
-        inv_step2(v, unit_slots + j * kSlotLd);     // row j was read only by this thread
+        inv_step2(v, row);                          // a slot row is read and rewritten by the same thread only
     }
     __syncthreads();
     float comb[24];
