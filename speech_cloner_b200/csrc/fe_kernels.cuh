@@ -344,7 +344,7 @@ k_fe_pass_a(const float* __restrict__ wav, Ragged rg, FeTables tb, FeParams prm,
     // ---- step 2 + |X|^2 (packed columns on the lowest thread ids, see step2_task)
     {
         int u2, c2;
-        step2_task(tid, UNITS, u2, c2);
+        step2_task<true>(tid, UNITS, u2, c2);
         cx<R> v[20];
         fwd_step2(v, sm.slots + u2 * kUnitSlots + c2 * kSlotLd);
         float* pa = sm.power + (2 * u2) * kBins;
@@ -525,7 +525,7 @@ k_fe_pass_a_persist(const float* __restrict__ wav, Ragged rg, int total_tiles, F
         bar_sync<1, CT>();
         {
             int u2, c2;
-            step2_task(tid, UNITS, u2, c2);
+            step2_task<true>(tid, UNITS, u2, c2);
             cx<R> v[20];
             fwd_step2(v, sm.slots + u2 * kUnitSlots + c2 * kSlotLd);
             float* pa = sm.power + (2 * u2) * kBins;

@@ -93,13 +93,33 @@ SC_HD void fwd_step2(cx<R> (&v)[20], const cx<R>* __restrict__ slot_row) {
 
 // Step-2 work assignment.  A step-2 task is (unit, column c); its inputs come from shared memory, so any
 // thread can run any task.  The packed columns c = 0 and c = 10 take a different code path than the
-// 18 one-frame columns: give them to the lowest thread ids so that only the first warp diverges instead
-// of every warp executing all three paths.
+// 18 one-frame columns: park them on the first lanes of the first two warps so that all other warps run
+// a single path instead of every warp executing all three.
+template <bool SPLIT>
 SC_HD void step2_task(int tid, int units, int& unit, int& c) {
-    if (tid < 2 * units) {
-        unit = tid >> 1;
-        c = (tid & 1) ? 10 : 0;
+    if (SPLIT) {
+        // c = 0 tasks on the first lanes of warp 0, c = 10 tasks on the first lanes of warp 1 (units <= 16): each
+        // of those two warps runs ONE packed path next to the generic one (measured best for the front-end)
+        if (tid < units) {
+            unit = tid; c = 0;
+            return;
+        }
+        if (tid >= 32 && tid < 32 + units) {
+            unit = tid - 32; c = 10;
+            return;
+        }
+        const int g = tid < 32 ? tid - units : tid - 2 * units;
+        unit = g / 18;
+        const int r = g - unit * 18;
+        c = r < 9 ? r + 1 : r + 2;
     } else {
+        // all packed columns on the lowest thread ids: with 16 units warp 0 is entirely packed columns and
+        // warps 1..9 run only the generic path (measured best for Griffin-Lim)
+        if (tid < 2 * units) {
+            unit = tid >> 1;
+            c = (tid & 1) ? 10 : 0;
+            return;
+        }
         const int g = tid - 2 * units;
         unit = g / 18;
         const int r = g - unit * 18;

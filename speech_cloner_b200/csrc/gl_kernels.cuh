@@ -59,7 +59,8 @@ struct GlSmem {
     float span[kGlSpan];
     float win_half[kNfft];
     float win_inv[kNfft];
-    cxf slots[kFeUnits * kUnitSlots];   // reused as seg[16][480] floats after the inverse
+    cxf slots[kFeUnits * kUnitSlots];
+    float seg[kFeUnits * kGlSeg];       // windowed inverse transforms of the units (A + B pre-added), 480 each
 };
 
 template <bool INIT>
@@ -132,7 +133,7 @@ k_gl_iter(const GlJob* __restrict__ jobs, int n_jobs, const int32_t* __restrict_
     {
         // step-2 task of this thread (packed columns on warp 0, see step2_task) and its unit's two frames
         int u2, c2;
-        step2_task(tid, kFeUnits, u2, c2);
+        step2_task<false>(tid, kFeUnits, u2, c2);
         const int ga = t0 + 2 * u2, gb = ga + 1;
         const bool wa = ga >= job.f_lo && ga < job.f_lo + job.f_cnt && ga < T;
         const bool wb = gb >= job.f_lo && gb < job.f_lo + job.f_cnt && gb < T;
@@ -164,8 +165,7 @@ k_gl_iter(const GlJob* __restrict__ jobs, int n_jobs, const int32_t* __restrict_
             comb[m] = a;
         }
     }
-    __syncthreads();                                 // every slot has been consumed
-    float* seg = reinterpret_cast<float*>(sm.slots);
+    float* seg = sm.seg;
     {
         float* __restrict__ dst = seg + unit * kGlSeg + j;
 #pragma unroll
