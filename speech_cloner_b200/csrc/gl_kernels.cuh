@@ -193,6 +193,170 @@ k_gl_iter(const GlJob* __restrict__ jobs, int n_jobs, const int32_t* __restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent form of the iteration kernel: a CTA loops over tiles of a host-built (job, tile) table, keeps
+// the windows / twiddles resident and requests the NEXT tile's 2 880 waveform samples with cp.async while
+// it computes the current one (edge tiles, which need reflect padding, are staged synchronously).  The
+// per-tile arithmetic is the body of k_gl_iter<false>, so both kernels give bit-identical waveforms.
+struct GlSmemP {
+    alignas(16) float span[2][kGlSpan];
+    float win_half[kNfft];
+    float win_inv[kNfft];
+    cxf slots[kFeUnits * kUnitSlots];
+    float seg[kFeUnits * kGlSeg];
+};
+
+struct GlGeom {
+    int T, Lw, out_first, out_end, t0, span0;
+};
+__device__ __forceinline__ GlGeom gl_geom(const GlJob& job, int tile_in_job) {
+    GlGeom g;
+    g.T = job.T;
+    g.Lw = kHop * (job.T - 1);
+    g.out_first = (int)job.out_first;
+    g.out_end = (int)(job.out_first + job.out_count);
+    const int p_first = ((g.out_first + kNfft / 2) / kGlOut) * kGlOut;
+    const int o = p_first + tile_in_job * kGlOut;
+    g.t0 = o / kHop - 4;
+    g.span0 = g.t0 * kHop;
+    return g;
+}
+
+__global__ void __launch_bounds__(kFeThreads, 2)
+k_gl_iter_persist(const GlJob* __restrict__ jobs, const int2* __restrict__ tile_tab, int n_tiles, GlTables tb,
+                  const float* __restrict__ amp, const float* __restrict__ wav_in, float* __restrict__ wav_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GlSmemP& sm = *reinterpret_cast<GlSmemP*>(smem_raw);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kNfft; i += kFeThreads) {
+        sm.win_half[i] = tb.win_half[i];
+        sm.win_inv[i] = tb.win_inv[i];
+    }
+    const int unit = tid / kUnitThreads;
+    const int j = tid - unit * kUnitThreads;
+    Twiddle tw;
+    load_twiddles(tw, tb.w400, j);
+    cxf* unit_slots = sm.slots + unit * kUnitSlots;
+
+    auto stage = [&](int tile, int b) {
+        const int2 e = __ldg(tile_tab + tile);
+        const GlJob jb = jobs[e.x];
+        const GlGeom g = gl_geom(jb, e.y);
+        const float* __restrict__ src = wav_in + jb.wav_in_off;
+        const int q0 = g.span0 - kNfft / 2;
+        const int in_first = (int)jb.wav_in_first, in_end = (int)(jb.wav_in_first + jb.wav_in_count);
+        float* dst = sm.span[b];
+        if (q0 >= 0 && q0 + kGlSpan <= g.Lw && q0 >= in_first && q0 + kGlSpan <= in_end) {
+            const float* __restrict__ s0 = src + (q0 - in_first);
+            if ((reinterpret_cast<uintptr_t>(s0) & 15) == 0) {
+                for (int i = tid; i < kGlSpan / 4; i += kFeThreads) cp_async16(dst + 4 * i, s0 + 4 * i);
+            } else {
+                for (int i = tid; i < kGlSpan; i += kFeThreads) cp_async4(dst + i, s0 + i);
+            }
+        } else {
+            for (int i = tid; i < kGlSpan; i += kFeThreads) {
+                const int r = (int)reflect_idx((int64_t)q0 + i, g.Lw) - in_first;
+                dst[i] = (r >= 0 && r < in_end - in_first) ? __ldg(src + r) : 0.0f;
+            }
+        }
+    };
+
+    int tile = blockIdx.x, b = 0;
+    if (tile < n_tiles) stage(tile, 0);
+    cp_async_wait_all();
+    __syncthreads();
+#pragma unroll 1
+    for (; tile < n_tiles; tile += gridDim.x, b ^= 1) {
+        if (tile + (int)gridDim.x < n_tiles) stage(tile + gridDim.x, b ^ 1);
+        const int2 e = __ldg(tile_tab + tile);
+        const GlJob job = jobs[e.x];
+        const GlGeom g = gl_geom(job, e.y);
+        const int T = g.T, Lw = g.Lw, out_first = g.out_first, out_end = g.out_end, t0 = g.t0, span0 = g.span0;
+        const float* __restrict__ span = sm.span[b];
+
+        // Frames of this unit.  A frame that does not exist (outside [0, T) or outside the rows this job
+        // holds) is fed exact zeros end to end: the two frames of a pair share one packed transform, so
+        // any garbage in the partner would change the rounding of the real frame and break the
+        // bit-identity of time-chunked runs.
+        const int fa = t0 + 2 * unit, fb = fa + 1;
+        const bool va = fa >= job.f_lo && fa < job.f_lo + job.f_cnt && fa < T;
+        const bool vb = fb >= job.f_lo && fb < job.f_lo + job.f_cnt && fb < T;
+        const float ka = va ? 1.0f : 0.0f, kb = vb ? 1.0f : 0.0f;
+        {
+            float s[24];
+            const float* __restrict__ src = span + unit * (2 * kHop) + j;
+    #pragma unroll
+            for (int m = 0; m < 24; ++m) s[m] = src[20 * m];
+            cxf z[20];
+    #pragma unroll
+            for (int n1 = 0; n1 < 20; ++n1) {
+                const float w = sm.win_half[20 * n1 + j];
+                z[n1] = mk<float>(s[n1] * (w * ka), s[n1 + 4] * (w * kb));
+            }
+            fwd_step1(z, tw, unit_slots + j);
+            __syncthreads();
+        }
+        {
+            // step-2 task of this thread (packed columns on warp 0, see step2_task) and its unit's two frames
+            int u2, c2;
+            step2_task<false>(tid, kFeUnits, u2, c2);
+            const int ga = t0 + 2 * u2, gb = ga + 1;
+            const bool wa = ga >= job.f_lo && ga < job.f_lo + job.f_cnt && ga < T;
+            const bool wb = gb >= job.f_lo && gb < job.f_lo + job.f_cnt && gb < T;
+            const int64_t ra = job.amp_row0 + (wa ? ga - job.f_lo : 0);
+            const int64_t rb = job.amp_row0 + (wb ? gb - job.f_lo : 0);
+            const float* __restrict__ amp_a = wa ? amp + ra * kBins : tb.zero_row;
+            const float* __restrict__ amp_b = wb ? amp + rb * kBins : tb.zero_row;
+            cxf* row = sm.slots + u2 * kUnitSlots + c2 * kSlotLd;
+            cxf v[20];
+            fwd_step2(v, row);
+            gl_update(v, c2, amp_a, amp_b);
+            inv_step2(v, row);                          // a slot row is read and rewritten by the same thread only
+        }
+        __syncthreads();
+        float comb[24];
+        {
+            cxf h[20];
+            inv_step1(h, tw, unit_slots + j);
+    #pragma unroll
+            for (int m = 0; m < 24; ++m) {
+                float a = 0.f;
+                if (m < 20) a = h[m].x * sm.win_inv[20 * m + j];
+                if (m >= 4) a += h[m - 4].y * sm.win_inv[20 * (m - 4) + j];
+                comb[m] = a;
+            }
+        }
+        float* seg = sm.seg;
+        {
+            float* __restrict__ dst = seg + unit * kGlSeg + j;
+    #pragma unroll
+            for (int m = 0; m < 24; ++m) dst[20 * m] = comb[m];
+        }
+        __syncthreads();
+        // ---- ordered overlap-add gather + normalisation; local positions [320, 320 + kGlOut) are complete
+        {
+            float* __restrict__ dst = wav_out + job.wav_out_off;
+            // every output sample of an interior tile is covered by all 5 frames: periodic 1 / sum-square
+            const bool steady = t0 >= 0 && t0 + kGlFrames <= T;
+            for (int i = tid; i < kGlOut; i += kFeThreads) {
+                const int l = 320 + i;                                  // local padded offset in the tile
+                const int p = span0 + l;                                // padded position
+                const int s = p - kNfft / 2;                            // whole-signal sample index
+                if (s < out_first || s >= out_end || s >= Lw) continue;
+                int u_lo = l >= kGlSeg ? (l - kGlSeg) / (2 * kHop) + 1 : 0;
+                int u_hi = l / (2 * kHop);
+                if (u_hi > kFeUnits - 1) u_hi = kFeUnits - 1;
+                float acc = 0.f;
+                for (int uu = u_lo; uu <= u_hi; ++uu) acc += seg[uu * kGlSeg + (l - uu * 2 * kHop)];
+                const float nrm = steady ? __ldg(tb.inv_wss + (l % kHop)) : inv_wss_at(p, T, tb);
+                dst[s - out_first] = acc * nrm;
+            }
+        }
+        cp_async_wait_all();
+        __syncthreads();
+    }
+}
+
 // sqrt(mean((a - b)^2)) per job: the value the reference prints when verbose (:262-264)
 __global__ void __launch_bounds__(256) k_rms_delta_partial(const float* __restrict__ a, const float* __restrict__ b,
                                                           const GlJob* __restrict__ jobs, int n_jobs,

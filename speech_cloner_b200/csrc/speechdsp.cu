@@ -759,8 +759,15 @@ extern "C" int sc_griffinlim_batch(sc_plan* pl, const float* amp, const float* p
         prefix[u + 1] = (int32_t)t; rprefix[u + 1] = (int32_t)r;
         if (soff[u] + j.out_count > total) total = soff[u] + j.out_count;
     }
+    // (job, tile) table of the persistent iteration kernel
+    std::vector<int2> tile_tab;
+    if (pl->fast) {
+        tile_tab.reserve(prefix[n]);
+        for (int u = 0; u < n; ++u)
+            for (int k = 0; k < prefix[u + 1] - prefix[u]; ++k) tile_tab.push_back(make_int2(u, k));
+    }
     Blob b;
-    const size_t o_j = b.add(jobs), o_p = b.add(prefix), o_r = b.add(rprefix);
+    const size_t o_j = b.add(jobs), o_p = b.add(prefix), o_r = b.add(rprefix), o_tab = b.add(tile_tab);
     if (int rc = upload_blob(pl, b, st)) return rc;
     // ping-pong partner of `wav` + rms partials
     const size_t w_part = (sizeof(float) * (size_t)total + 255) & ~size_t(255);
@@ -774,8 +781,18 @@ extern "C" int sc_griffinlim_batch(sc_plan* pl, const float* amp, const float* p
     if (pl->profile) { if (int rc = prof_event(pl, 0, st)) return rc; pl->pev_kind = 2; pl->pev_iters = n_iters; }
     if (int rc = gl_launch(pl, true, dj, n, dp, prefix[n], amp, phase0, nullptr, buf(0), st)) return rc;
     if (pl->profile) if (int rc = prof_event(pl, 1, st)) return rc;
+    static int n_sm = 0;
+    if (pl->fast && n_sm == 0) {
+        SC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, pl->device));
+        SC_CUDA(cudaFuncSetAttribute(k_gl_iter_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GlSmemP)));
+    }
     for (int i = 1; i < n_iters; ++i) {
-        if (int rc = gl_launch(pl, false, dj, n, dp, prefix[n], amp, phase0, buf(i - 1), buf(i), st)) return rc;
+        if (pl->fast && prefix[n] > 0) {
+            const int grid = prefix[n] < 2 * n_sm ? prefix[n] : 2 * n_sm;
+            k_gl_iter_persist<<<grid, kFeThreads, sizeof(GlSmemP), st>>>(dj, at<int2>(pl, o_tab), prefix[n], gl_tables(pl), amp,
+                                                                         buf(i - 1), buf(i));
+            SC_LAUNCHED();
+        } else if (int rc = gl_launch(pl, false, dj, n, dp, prefix[n], amp, phase0, buf(i - 1), buf(i), st)) return rc;
         if (rms && rprefix[n] > 0) {
             k_rms_delta_partial<<<rprefix[n], 256, 0, st>>>(buf(i - 1), buf(i), dj, n, at<int32_t>(pl, o_r), rpart);
             SC_LAUNCHED();
