@@ -257,9 +257,18 @@ def main():
     names = ["k_abs_pairwise+k_gain_finalize", f"k_fe_pass_a<{'double' if args.precision == 'fp64' else 'float'}>", "k_fe_pass_b"]
     top = int(np.argmax(prof))
     fe_bytes = FE_BYTES_PER_FRAME * frames
+    try:                                   # DRAM bytes per launch from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            traffic_tab = json.load(f)
+    except Exception:
+        traffic_tab = {}
     achieved = fe_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": (sum(traffic_tab.get(n, float("nan")) for n in names) if traffic_tab else None),
+        "traffic_note": "DRAM read+write bytes of one step (all kernels), ncu --set full, profiles/r01_traffic.json; "
+                        "algorithmic bytes of the step: %d" % fe_bytes,
+        "kernel_traffic": traffic_tab.get(names[top]),
         "peak_source": peak_src,
         "definition": "1764 B/frame x frames of one step / summed device time of the step's kernels",
         "kernel": names[top],
@@ -365,14 +374,14 @@ def main():
                           "mean_abs_amp_norm 0.045, realse 1.0 (test.py:148-156)",
               "value": world * gl_audio / (gl_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": gl_ms,
               "ms_per_iteration": iter_ms, "l2": "flushed between timed steps; state stays L2-resident inside a step",
-              "roofline": {"bound": "hbm", "kernel": "k_gl_iter<false>", "peak": peak, "unit": "GB/s",
+              "roofline": {"bound": "hbm", "kernel": "k_gl_iter_persist", "peak": peak, "unit": "GB/s",
                            "achieved": GL_BYTES_PRIMARY * fr / (iter_ms * 1e-3) / 1e9,
                            "frac": GL_BYTES_PRIMARY * fr / (iter_ms * 1e-3) / 1e9 / peak,
                            "definition": "4020 B/frame-iteration (complex64 spectrogram state, SURVEY.md §8(d))",
                            "strict_achieved": GL_BYTES_STRICT * fr / (iter_ms * 1e-3) / 1e9,
                            "strict_frac": GL_BYTES_STRICT * fr / (iter_ms * 1e-3) / 1e9 / peak,
                            "strict_definition": "1444 B/frame-iteration (waveform state: what the kernel moves)",
-                           "traffic": None}}
+                           "traffic": traffic_tab.get("k_gl_iter_persist")}}
 
     # ---- long-form Griffin-Lim, configs[3]: one ~20 min spectrogram time-chunked over the ranks
     if gl is not None and args.gl_long:
