@@ -94,4 +94,89 @@ SC_HD void dft20(cx<R> (&v)[20]) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Real-input 20-point DFT (forward) and its Hermitian-input inverse, same Good-Thomas 4 x 5 graph with
+// the conjugate-symmetric half of the work removed (~94 instead of 224 instructions).
+//   forward:  Y[k] = sum_n x[n] exp(-2*pi*i*n*k/20),            k = 0..10  (Y[20-k] = conj Y[k])
+//   inverse:  x[n] = sum_{k=0..19} Y[k] exp(+2*pi*i*n*k/20)     with the Hermitian extension of Y[0..10];
+//             the imaginary parts of Y[0] and Y[10] are ignored.
+
+// 5-point DFT of real inputs: z0 real, z1 = (m1, -q1), z2 = (m2, -q2)  (z3 = conj z2, z4 = conj z1)
+template <typename R>
+SC_HD void rradix5(R a0, R a1, R a2, R a3, R a4, R& z0, cx<R>& z1, cx<R>& z2) {
+    constexpr R C1 = (R)0.30901699437494742410, C2 = (R)-0.80901699437494742410;
+    constexpr R S1 = (R)0.95105651629515357212, S2 = (R)0.58778525229247312917;
+    const R t1 = a1 + a4, t3 = a1 - a4, t2 = a2 + a3, t4 = a2 - a3;
+    z0 = a0 + t1 + t2;
+    z1 = mk<R>(sc_fma(C2, t2, sc_fma(C1, t1, a0)), -sc_fma(S2, t4, S1 * t3));
+    z2 = mk<R>(sc_fma(C1, t2, sc_fma(C2, t1, a0)), -sc_fma(-S1, t4, S2 * t3));
+}
+// inverse of rradix5: real outputs t[n] = z0 + 2 Re(z1 e^{+i n th}) + 2 Re(z2 e^{+2 i n th}), th = 2*pi/5
+template <typename R>
+SC_HD void rradix5_inv(R z0, cx<R> z1, cx<R> z2, R& t0, R& t1, R& t2, R& t3, R& t4) {
+    constexpr R C1 = (R)0.30901699437494742410, C2 = (R)-0.80901699437494742410;
+    constexpr R S1 = (R)0.95105651629515357212, S2 = (R)0.58778525229247312917;
+    const R u1 = z1.x + z1.x, u2 = z2.x + z2.x, w1 = z1.y + z1.y, w2 = z2.y + z2.y;
+    const R a = sc_fma(C2, u2, sc_fma(C1, u1, z0)), b = sc_fma(C1, u2, sc_fma(C2, u1, z0));
+    const R e = sc_fma(S2, w2, S1 * w1), f = sc_fma(-S1, w2, S2 * w1);
+    t0 = z0 + u1 + u2;
+    t1 = a - e; t4 = a + e;
+    t2 = b - f; t3 = b + f;
+}
+
+template <typename R>
+SC_HD void rdft20_fwd(const R (&x)[20], cx<R> (&Y)[11]) {
+    R t0[5], t2[5];
+    cx<R> t1[5];
+#pragma unroll
+    for (int n2 = 0; n2 < 5; ++n2) {
+        const R a0 = x[(0 + 4 * n2) % 20], a1 = x[(5 + 4 * n2) % 20], a2 = x[(10 + 4 * n2) % 20], a3 = x[(15 + 4 * n2) % 20];
+        const R r0 = a0 + a2, r1 = a0 - a2, r2 = a1 + a3, r3 = a1 - a3;
+        t0[n2] = r0 + r2;
+        t2[n2] = r0 - r2;
+        t1[n2] = mk<R>(r1, -r3);
+    }
+    R z0; cx<R> z1, z2;
+    // k1 = 0: k = 16*k2 mod 20 -> 0, 16, 12 (8 = conj 12, 4 = conj 16)
+    rradix5(t0[0], t0[1], t0[2], t0[3], t0[4], z0, z1, z2);
+    Y[0] = mk<R>(z0, (R)0);
+    Y[4] = mk<R>(z1.x, -z1.y);
+    Y[8] = mk<R>(z2.x, -z2.y);
+    // k1 = 2: k = 10 + 16*k2 mod 20 -> 10, 6, 2
+    rradix5(t2[0], t2[1], t2[2], t2[3], t2[4], z0, z1, z2);
+    Y[10] = mk<R>(z0, (R)0);
+    Y[6] = z1;
+    Y[2] = z2;
+    // k1 = 1: k = 5 + 16*k2 mod 20 -> 5, 1, 17, 13, 9 (3 = conj 17, 7 = conj 13)
+    radix5<false>(t1[0], t1[1], t1[2], t1[3], t1[4]);
+    Y[5] = t1[0];
+    Y[1] = t1[1];
+    Y[3] = mk<R>(t1[2].x, -t1[2].y);
+    Y[7] = mk<R>(t1[3].x, -t1[3].y);
+    Y[9] = t1[4];
+}
+
+template <typename R>
+SC_HD void rdft20_inv(const cx<R> (&Y)[11], R (&x)[20]) {
+    R t0[5], t2[5];
+    cx<R> t1[5];
+    rradix5_inv(Y[0].x, mk<R>(Y[4].x, -Y[4].y), mk<R>(Y[8].x, -Y[8].y), t0[0], t0[1], t0[2], t0[3], t0[4]);
+    rradix5_inv(Y[10].x, Y[6], Y[2], t2[0], t2[1], t2[2], t2[3], t2[4]);
+    t1[0] = Y[5]; t1[1] = Y[1];
+    t1[2] = mk<R>(Y[3].x, -Y[3].y);
+    t1[3] = mk<R>(Y[7].x, -Y[7].y);
+    t1[4] = Y[9];
+    radix5<true>(t1[0], t1[1], t1[2], t1[3], t1[4]);
+#pragma unroll
+    for (int n2 = 0; n2 < 5; ++n2) {
+        // inverse 4-point over k1 with T3 = conj T1: a0 = T0+T2+2ReT1, a2 = T0+T2-2ReT1, a1 = T0-T2-2ImT1, a3 = T0-T2+2ImT1
+        const R s = t0[n2] + t2[n2], d = t0[n2] - t2[n2];
+        const R re2 = t1[n2].x + t1[n2].x, im2 = t1[n2].y + t1[n2].y;
+        x[(0 + 4 * n2) % 20] = s + re2;
+        x[(10 + 4 * n2) % 20] = s - re2;
+        x[(5 + 4 * n2) % 20] = d - im2;
+        x[(15 + 4 * n2) % 20] = d + im2;
+    }
+}
+
 }  // namespace scdsp

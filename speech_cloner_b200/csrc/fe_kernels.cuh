@@ -254,7 +254,7 @@ struct FeSmemA {
     static constexpr int SPAN = kHop * (F - 1) + kNfft;  // samples a tile touches
     static constexpr int THREADS = UNITS * kUnitThreads;
     R span[SPAN];                              // pre-emphasised, reflect-padded samples of the tile
-    R win[kNfft];
+    R win[kNfft];                              // full analysis window (2 * win_half)
     cx<R> slots[UNITS * kUnitSlots];           // step-1 -> step-2 exchange
     cx<R> w400[sizeof(R) == 8 ? kNfft : 1];    // twiddle table (float64 path reads it on use)
     float power[F * kBins];                    // |X|^2, row = frame
@@ -309,11 +309,11 @@ k_fe_pass_a(const float* __restrict__ wav, Ragged rg, FeTables tb, FeParams prm,
         }
         if (kF64) {
             for (int i = tid; i < kNfft; i += THREADS) {
-                sm.win[i] = (R)tb.win_half_d[i];
+                sm.win[i] = (R)(2.0 * tb.win_half_d[i]);
                 sm.w400[i] = mk<R>((R)tb.w400_d[i].x, (R)tb.w400_d[i].y);
             }
         } else {
-            for (int i = tid; i < kNfft; i += THREADS) sm.win[i] = (R)tb.win_half[i];
+            for (int i = tid; i < kNfft; i += THREADS) sm.win[i] = (R)(2.0f * tb.win_half[i]);
         }
         for (int i = tid; i < kBins; i += THREADS) sm.mel_w[i] = tb.mel_w[i];
         for (int i = tid; i < n_mels + 2; i += THREADS) sm.mel_istart[i] = tb.mel_istart[i];
@@ -332,13 +332,14 @@ k_fe_pass_a(const float* __restrict__ wav, Ragged rg, FeTables tb, FeParams prm,
         const R* __restrict__ src = sm.span + unit * (2 * kHop) + j;
 #pragma unroll
         for (int m = 0; m < 24; ++m) s[m] = src[20 * m];
-        cx<R> z[20];
+        R xa[20], xb[20];
 #pragma unroll
         for (int n1 = 0; n1 < 20; ++n1) {
             const R w = sm.win[20 * n1 + j];
-            z[n1] = mk<R>(s[n1] * w, s[n1 + 4] * w);
+            xa[n1] = s[n1] * w;
+            xb[n1] = s[n1 + 4] * w;
         }
-        fwd_step1(z, tw, unit_slots + j);
+        fwd_step1_real(xa, xb, tw, unit_slots + j);
     }
     __syncthreads();
     // ---- step 2 + |X|^2 (packed columns on the lowest thread ids, see step2_task)
@@ -471,11 +472,11 @@ k_fe_pass_a_persist(const float* __restrict__ wav, Ragged rg, int total_tiles, F
     // ================================== compute warps ==================================
     if (kF64) {
         for (int i = tid; i < kNfft; i += CT) {
-            sm.win[i] = (R)tb.win_half_d[i];
+            sm.win[i] = (R)(2.0 * tb.win_half_d[i]);
             sm.w400[i] = mk<R>((R)tb.w400_d[i].x, (R)tb.w400_d[i].y);
         }
     } else {
-        for (int i = tid; i < kNfft; i += CT) sm.win[i] = (R)tb.win_half[i];
+        for (int i = tid; i < kNfft; i += CT) sm.win[i] = (R)(2.0f * tb.win_half[i]);
     }
     for (int i = tid; i < kBins; i += CT) sm.mel_w[i] = tb.mel_w[i];
     for (int i = tid; i < n_mels + 2; i += CT) sm.mel_istart[i] = tb.mel_istart[i];
@@ -514,13 +515,14 @@ k_fe_pass_a_persist(const float* __restrict__ wav, Ragged rg, int total_tiles, F
                     s[m] = (R)((double)cur - c * (double)prev);
                 }
             }
-            cx<R> z[20];
+            R xa[20], xb[20];
 #pragma unroll
             for (int n1 = 0; n1 < 20; ++n1) {
                 const R w = sm.win[20 * n1 + j];
-                z[n1] = mk<R>(s[n1] * w, s[n1 + 4] * w);
+                xa[n1] = s[n1] * w;
+                xb[n1] = s[n1 + 4] * w;
             }
-            fwd_step1(z, tw, unit_slots + j);
+            fwd_step1_real(xa, xb, tw, unit_slots + j);
         }
         bar_sync<1, CT>();
         {

@@ -275,4 +275,39 @@ SC_HD void inv_step1(cx<R> (&h)[20], const TW& t, const cx<R>* __restrict__ slot
     dft20<true>(h);
 }
 
+// ---- real-input variants of step 1 (forward) and step 1' (inverse): two real 20-point DFTs instead of one packed
+//      complex one + Hermitian split.  xa / xb are the FULL-window samples of frames A / B at 20*n1 + j.
+template <typename R, typename TW>
+SC_HD void fwd_step1_real(const R (&xa)[20], const R (&xb)[20], const TW& t, cx<R>* __restrict__ slot_col) {
+    cx<R> ya[11], yb[11];
+    rdft20_fwd(xa, ya);
+    rdft20_fwd(xb, yb);
+    slot_col[0] = mk<R>(ya[0].x, yb[0].x);
+    slot_col[10 * kSlotLd] = cmul(mk<R>(ya[10].x, yb[10].x), t.get10());
+#pragma unroll
+    for (int k1 = 1; k1 < 10; ++k1) {
+        const cx<R> w = t.get(k1);
+        slot_col[k1 * kSlotLd] = cmul(ya[k1], w);
+        slot_col[(10 + k1) * kSlotLd] = cmul(yb[k1], w);
+    }
+}
+
+// On return xa[n1] = 400 * xA[20*n1 + j], xb[n1] = 400 * xB[20*n1 + j].
+template <typename R, typename TW>
+SC_HD void inv_step1_real(R (&xa)[20], R (&xb)[20], const TW& t, const cx<R>* __restrict__ slot_col) {
+    cx<R> ha[11], hb[11];
+    const cx<R> s0 = slot_col[0];
+    const cx<R> s10 = cmulc(slot_col[10 * kSlotLd], t.get10());
+    ha[0] = mk<R>(s0.x, (R)0); hb[0] = mk<R>(s0.y, (R)0);
+    ha[10] = mk<R>(s10.x, (R)0); hb[10] = mk<R>(s10.y, (R)0);
+#pragma unroll
+    for (int k1 = 1; k1 < 10; ++k1) {
+        const cx<R> w = t.get(k1);
+        ha[k1] = cmulc(slot_col[k1 * kSlotLd], w);
+        hb[k1] = cmulc(slot_col[(10 + k1) * kSlotLd], w);
+    }
+    rdft20_inv(ha, xa);
+    rdft20_inv(hb, xb);
+}
+
 }  // namespace scdsp

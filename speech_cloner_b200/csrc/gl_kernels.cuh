@@ -84,7 +84,7 @@ k_gl_iter(const GlJob* __restrict__ jobs, int n_jobs, const int32_t* __restrict_
     const int span0 = t0 * kHop;                               // padded position of span[0]
 
     for (int i = tid; i < kNfft; i += kFeThreads) {
-        sm.win_half[i] = tb.win_half[i];
+        sm.win_half[i] = 2.0f * tb.win_half[i];       // full Hann window
         sm.win_inv[i] = tb.win_inv[i];
     }
     if (!INIT) {
@@ -121,13 +121,14 @@ k_gl_iter(const GlJob* __restrict__ jobs, int n_jobs, const int32_t* __restrict_
         const float* __restrict__ src = sm.span + unit * (2 * kHop) + j;
 #pragma unroll
         for (int m = 0; m < 24; ++m) s[m] = src[20 * m];
-        cxf z[20];
+        float xa[20], xb[20];
 #pragma unroll
         for (int n1 = 0; n1 < 20; ++n1) {
             const float w = sm.win_half[20 * n1 + j];
-            z[n1] = mk<float>(s[n1] * (w * ka), s[n1 + 4] * (w * kb));
+            xa[n1] = s[n1] * (w * ka);
+            xb[n1] = s[n1 + 4] * (w * kb);
         }
-        fwd_step1(z, tw, unit_slots + j);
+        fwd_step1_real(xa, xb, tw, unit_slots + j);
         __syncthreads();
     }
     {
@@ -155,13 +156,13 @@ k_gl_iter(const GlJob* __restrict__ jobs, int n_jobs, const int32_t* __restrict_
     __syncthreads();
     float comb[24];
     {
-        cxf h[20];
-        inv_step1(h, tw, unit_slots + j);
+        float ya[20], yb[20];
+        inv_step1_real(ya, yb, tw, unit_slots + j);
 #pragma unroll
         for (int m = 0; m < 24; ++m) {
             float a = 0.f;
-            if (m < 20) a = h[m].x * sm.win_inv[20 * m + j];
-            if (m >= 4) a += h[m - 4].y * sm.win_inv[20 * (m - 4) + j];
+            if (m < 20) a = ya[m] * sm.win_inv[20 * m + j];
+            if (m >= 4) a += yb[m - 4] * sm.win_inv[20 * (m - 4) + j];
             comb[m] = a;
         }
     }
@@ -229,7 +230,7 @@ k_gl_iter_persist(const GlJob* __restrict__ jobs, const int2* __restrict__ tile_
     GlSmemP& sm = *reinterpret_cast<GlSmemP*>(smem_raw);
     const int tid = threadIdx.x;
     for (int i = tid; i < kNfft; i += kFeThreads) {
-        sm.win_half[i] = tb.win_half[i];
+        sm.win_half[i] = 2.0f * tb.win_half[i];       // full Hann window
         sm.win_inv[i] = tb.win_inv[i];
     }
     const int unit = tid / kUnitThreads;
@@ -287,13 +288,14 @@ k_gl_iter_persist(const GlJob* __restrict__ jobs, const int2* __restrict__ tile_
             const float* __restrict__ src = span + unit * (2 * kHop) + j;
     #pragma unroll
             for (int m = 0; m < 24; ++m) s[m] = src[20 * m];
-            cxf z[20];
+            float xa[20], xb[20];
     #pragma unroll
             for (int n1 = 0; n1 < 20; ++n1) {
                 const float w = sm.win_half[20 * n1 + j];
-                z[n1] = mk<float>(s[n1] * (w * ka), s[n1 + 4] * (w * kb));
+                xa[n1] = s[n1] * (w * ka);
+                xb[n1] = s[n1 + 4] * (w * kb);
             }
-            fwd_step1(z, tw, unit_slots + j);
+            fwd_step1_real(xa, xb, tw, unit_slots + j);
             __syncthreads();
         }
         {
@@ -316,13 +318,13 @@ k_gl_iter_persist(const GlJob* __restrict__ jobs, const int2* __restrict__ tile_
         __syncthreads();
         float comb[24];
         {
-            cxf h[20];
-            inv_step1(h, tw, unit_slots + j);
+            float ya[20], yb[20];
+            inv_step1_real(ya, yb, tw, unit_slots + j);
     #pragma unroll
             for (int m = 0; m < 24; ++m) {
                 float a = 0.f;
-                if (m < 20) a = h[m].x * sm.win_inv[20 * m + j];
-                if (m >= 4) a += h[m - 4].y * sm.win_inv[20 * (m - 4) + j];
+                if (m < 20) a = ya[m] * sm.win_inv[20 * m + j];
+                if (m >= 4) a += yb[m - 4] * sm.win_inv[20 * (m - 4) + j];
                 comb[m] = a;
             }
         }

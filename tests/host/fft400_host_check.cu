@@ -60,6 +60,46 @@ static int check(const char* name, double tol_pow, double tol_rt) {
     printf("[%s] power max %.4g  max abs err %.3g  rel %.3g\n", name, pmax, perr, perr / pmax);
     int fail = perr / pmax > tol_pow;
 
+    // ---------------- real-input step 1 / step 1' (two real 20-point DFTs) against the same references
+    {
+        std::vector<cx<R>> slots2(kUnitSlots);
+        for (int j = 0; j < 20; ++j) {
+            R a[20], b[20];
+            for (int n1 = 0; n1 < 20; ++n1) { a[n1] = (R)xa[20 * n1 + j]; b[n1] = (R)xb[20 * n1 + j]; }
+            fwd_step1_real(a, b, twt[j], &slots2[j]);
+        }
+        double serr = 0, smax = 0;
+        for (int i = 0; i < kUnitSlots; ++i) {
+            if (i % kSlotLd == 20) continue;                      // padding column
+            serr = fmax(serr, fmax(fabs((double)slots2[i].x - (double)slots[i].x), fabs((double)slots2[i].y - (double)slots[i].y)));
+            smax = fmax(smax, fmax(fabs((double)slots[i].x), fabs((double)slots[i].y)));
+        }
+        printf("[%s] real step 1 vs packed step 1: max slot diff %.3g (max %.3g)\n", name, serr, smax);
+        fail |= serr / smax > tol_rt * 50 + 1e-15;
+        std::vector<float> pa2(kBins, -1.f), pb2(kBins, -1.f);
+        double rerr = 0;
+        for (int c = 0; c < 20; ++c) {
+            cx<R> v[20];
+            fwd_step2(v, &slots2[c * kSlotLd]);
+            store_power(v, c, pa2.data(), pb2.data());
+            inv_step2(v, &slots2[c * kSlotLd]);
+        }
+        for (int k = 0; k < kBins; ++k) rerr = fmax(rerr, fmax(fabs(pa2[k] - pa[k]), fabs(pb2[k] - pb[k])));
+        printf("[%s] real path power vs packed path power: max diff %.3g\n", name, rerr);
+        fail |= rerr / pmax > tol_pow;
+        double rt = 0;
+        for (int j = 0; j < 20; ++j) {
+            R a[20], b[20];
+            inv_step1_real(a, b, tw[j], &slots2[j]);
+            for (int n1 = 0; n1 < 20; ++n1) {
+                rt = fmax(rt, fabs((double)a[n1] / 400.0 - xa[20 * n1 + j]));
+                rt = fmax(rt, fabs((double)b[n1] / 400.0 - xb[20 * n1 + j]));
+            }
+        }
+        printf("[%s] real path forward -> inverse round trip: max abs err %.3g\n", name, rt);
+        fail |= rt > tol_rt;
+    }
+
     // ---------------- forward -> gl_update with A = |X| (identity) -> inverse == input
     std::vector<float> ampa(kBins), ampb(kBins), pha(kBins), phb(kBins);
     for (int k = 0; k < kBins; ++k) {
