@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspeechdsp.so")
+LIB_PATH = os.environ.get("SPEECHDSP_LIB") or os.path.join(_HERE, "libspeechdsp.so")   # override: A/B-testing builds
 
 SC_OK = 0
 SC_ERR_INVALID = -1

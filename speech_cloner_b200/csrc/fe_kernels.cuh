@@ -183,11 +183,23 @@ __device__ __forceinline__ void fe_epilogue_a(const float* __restrict__ power, i
     float p_max = 0.f, p_min = __int_as_float(0x7f800000), m_max = 0.f, m_min = __int_as_float(0x7f800000);
     {
         const int n = nfr * bins;
-        for (int e = tid; e < n; e += THREADS) {
-            const float p = power[e];
-            p_max = fmaxf(p_max, p);
-            p_min = fminf(p_min, p);
-            pdb_dst[e] = db10(fmaxf(p, 1e-10f));
+        if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(pdb_dst) & 15) == 0 && (reinterpret_cast<uintptr_t>(power) & 15) == 0) {
+            const float4* __restrict__ p4 = reinterpret_cast<const float4*>(power);      // full tiles: 128-bit smem reads / stores
+            float4* __restrict__ d4 = reinterpret_cast<float4*>(pdb_dst);
+            for (int e = tid; e < (n >> 2); e += THREADS) {
+                const float4 p = p4[e];
+                p_max = fmaxf(fmaxf(p_max, fmaxf(p.x, p.y)), fmaxf(p.z, p.w));
+                p_min = fminf(fminf(p_min, fminf(p.x, p.y)), fminf(p.z, p.w));
+                d4[e] = make_float4(db10(fmaxf(p.x, 1e-10f)), db10(fmaxf(p.y, 1e-10f)), db10(fmaxf(p.z, 1e-10f)),
+                                    db10(fmaxf(p.w, 1e-10f)));
+            }
+        } else {
+            for (int e = tid; e < n; e += THREADS) {
+                const float p = power[e];
+                p_max = fmaxf(p_max, p);
+                p_min = fminf(p_min, p);
+                pdb_dst[e] = db10(fmaxf(p, 1e-10f));
+            }
         }
     }
     // thread = (frame, band chunk); every lane of a warp walks the same bins => uniform control flow
