@@ -10,7 +10,7 @@ constexpr int kFeThreads = 320;        // 16 units x 20 threads
 constexpr int kFeUnits = 16;
 constexpr int kFeFrames = 32;          // frames per front-end tile (one round)
 constexpr int kFeSpan = kHop * (kFeFrames - 1) + 400;   // 2880 staged samples per tile
-constexpr int kMaxMelChunks = 8;
+constexpr int kMaxMelChunks = 10;   // 16 frames x 10 chunks = all 160 compute threads of a pass-A tile
 constexpr int kMaxMels = 128;
 
 // per-utterance record, device resident

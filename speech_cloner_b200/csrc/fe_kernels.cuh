@@ -49,7 +49,10 @@ struct FeParams {
 // that a subtree has <= kAbsSubtree samples), expands it into a 255-node heap in shared memory,
 // reduces the leaves with 8-lane groups and folds the heap bottom-up; k_gain_finalize folds the top
 // D levels.  Verified bitwise against numpy in tests/test_gpu_frontend.py::test_gain_matches_numpy.
-constexpr int kAbsSubtree = 8000;
+#ifndef SC_ABS_SUBTREE
+#define SC_ABS_SUBTREE 8000
+#endif
+constexpr int kAbsSubtree = SC_ABS_SUBTREE;
 constexpr int kAbsThreads = 256;
 
 __host__ __device__ inline int abs_depth(int64_t n) {
@@ -560,8 +563,14 @@ k_fe_pass_a_persist(const float* __restrict__ wav, Ragged rg, int total_tiles, F
 //   MFCC     : DCT-II (:176-179) with the even/odd symmetry of its rows: coefficient q uses
 //              s[n] = x[n] + x[N-1-n] (q even) or d[n] = x[n] - x[N-1-n] (q odd), n < N/2, which
 //              halves the multiply-adds; c0 shift (:221), scale (:224), delta (:226-228), clip (:238)
-constexpr int kFbFrames = 100;
-constexpr int kFbThreads = 256;
+#ifndef SC_FB_FRAMES
+#define SC_FB_FRAMES 20
+#endif
+#ifndef SC_FB_THREADS
+#define SC_FB_THREADS 128
+#endif
+constexpr int kFbFrames = SC_FB_FRAMES;      // multiple of 4 (16-byte aligned power-dB tiles)
+constexpr int kFbThreads = SC_FB_THREADS;
 
 struct FbLayout {        // shared-memory carve-up, identical on host and device
     int half, ne_pad, no_pad, sd_ld, cc_ld;

@@ -211,7 +211,9 @@ static MelSparse build_mel(int sr, int n_fft, int n_mels) {
     // balance the band chunks by cost
     std::vector<double> cost(n_mels + 1);
     double total = 0;
-    for (int i = 0; i <= n_mels; ++i) { cost[i] = 3.0 * (ms.istart[i + 1] - ms.istart[i]) + 12.0; total += cost[i]; }
+    double band_cost = 20.0;                                  // instructions per closed band relative to 3 per bin
+    if (const char* e = getenv("SC_MEL_BAND_COST")) band_cost = atof(e);
+    for (int i = 0; i <= n_mels; ++i) { cost[i] = 3.0 * (ms.istart[i + 1] - ms.istart[i]) + band_cost; total += cost[i]; }
     ms.chunk.assign(kMaxMelChunks + 1, n_mels);
     ms.chunk[0] = 0;
     double run = 0; int c = 1;
