@@ -240,7 +240,7 @@ k_gl_iter_persist(const GlJob* __restrict__ jobs, const int2* __restrict__ tile_
     cxf* unit_slots = sm.slots + unit * kUnitSlots;
 
     auto stage = [&](int tile, int b) {
-        const int2 e = __ldg(tile_tab + tile);
+        const int2 e = tile_tab ? __ldg(tile_tab + tile) : make_int2(0, tile);   // no table: one job, tile = index
         const GlJob jb = jobs[e.x];
         const GlGeom g = gl_geom(jb, e.y);
         const float* __restrict__ src = wav_in + jb.wav_in_off;
@@ -269,7 +269,7 @@ k_gl_iter_persist(const GlJob* __restrict__ jobs, const int2* __restrict__ tile_
 #pragma unroll 1
     for (; tile < n_tiles; tile += gridDim.x, b ^= 1) {
         if (tile + (int)gridDim.x < n_tiles) stage(tile + gridDim.x, b ^ 1);
-        const int2 e = __ldg(tile_tab + tile);
+        const int2 e = tile_tab ? __ldg(tile_tab + tile) : make_int2(0, tile);
         const GlJob job = jobs[e.x];
         const GlGeom g = gl_geom(job, e.y);
         const int T = g.T, Lw = g.Lw, out_first = g.out_first, out_end = g.out_end, t0 = g.t0, span0 = g.span0;

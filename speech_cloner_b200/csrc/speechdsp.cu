@@ -829,6 +829,19 @@ extern "C" int sc_griffinlim_chunk_step(sc_plan* pl, const float* amp, const flo
     Blob b;
     const size_t o_j = b.add(&j, 1), o_p = b.add(prefix, 2);
     if (int rc = upload_blob(pl, b, st)) return rc;
+    if (pl->fast && !phase0 && tiles > 0) {
+        // same persistent iteration kernel as sc_griffinlim_batch (one job: no tile table needed)
+        static int n_sm = 0;
+        if (n_sm == 0) {
+            SC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, pl->device));
+            SC_CUDA(cudaFuncSetAttribute(k_gl_iter_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GlSmemP)));
+        }
+        const int grid = tiles < 2 * n_sm ? (int)tiles : 2 * n_sm;
+        k_gl_iter_persist<<<grid, kFeThreads, sizeof(GlSmemP), st>>>(at<GlJob>(pl, o_j), nullptr, (int)tiles, gl_tables(pl), amp,
+                                                                     wav_in, wav_out);
+        SC_LAUNCHED();
+        return SC_OK;
+    }
     return gl_launch(pl, phase0 != nullptr, at<GlJob>(pl, o_j), 1, at<int32_t>(pl, o_p), (int)tiles, amp, phase0,
                      wav_in, wav_out, st);
 }
