@@ -174,6 +174,11 @@ __global__ void __launch_bounds__(128) k_gain_finalize(Ragged rg, const int64_t*
 //   raw power dB (:157 without the top_db clip)  -> pdb_dst  (coalesced)
 //   sparse Slaney mel (:160-169) + raw amplitude_to_db (:172) -> mel_dst
 //   utterance max / min of the power and of the mel power   -> stat (order-independent atomics)
+#ifndef SC_MEL_UNROLL
+#define SC_MEL_UNROLL 1
+#endif
+constexpr int kMelUnroll = SC_MEL_UNROLL;
+
 template <int THREADS, int BAR = 0>
 __device__ __forceinline__ void fe_epilogue_a(const float* __restrict__ power, int F, int bins, int nfr,
                                               const float2* __restrict__ mel_w_s, const int32_t* __restrict__ istart_s,
@@ -216,6 +221,7 @@ __device__ __forceinline__ void fe_epilogue_a(const float* __restrict__ power, i
             for (int i = mb; i <= me; ++i) {
                 float a_up = 0.f, a_dn = 0.f;
                 const int k1 = istart_s[i + 1];
+#pragma unroll kMelUnroll           // average trip count is 2.5: unrolling only adds prologue / remainder control code
                 for (int k = istart_s[i]; k < k1; ++k) {
                     const float p = prow[k];
                     const float2 w = mel_w_s[k];
