@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "fe_kernels.cuh"
+#include "fe_ws.cuh"
 #include "gl_kernels.cuh"
 #include "generic_kernels.cuh"
 
@@ -121,6 +122,10 @@ struct sc_plan {
     int pev_groups = 0;
     int pev_kind = 0;        // 1 = front-end (gain | pass A | pass B), 2 = Griffin-Lim (init | iterations)
     int pev_iters = 0;
+    WsMelParam ws_mel{};     // band / bin ranges of the epilogue warps of k_fe_pass_a_ws
+    const int4* ws_brec = nullptr;  // per-band (first tap, float4 blocks, weight offset)
+    const float* ws_wt = nullptr;   // padded filterbank weights
+    bool use_ws = true;      // warp-specialised pass A (env SC_FE_WS=0 selects the older persistent kernel)
     int64_t fe_group_frames = int64_t(1) << 60;   // frames per front-end group (env SC_FE_GROUP_FRAMES); measured: grouping for L2 residency only adds launch latency, so off by default
 };
 
@@ -289,6 +294,49 @@ extern "C" int sc_plan_create(const sc_params* p, sc_plan** out) {
     }
     std::vector<float> inv_wss = build_inv_wss(pl->gl_window, n_fft, p->hop_length);
     MelSparse ms = build_mel(p->sample_rate, n_fft, p->n_mels);
+    std::vector<int4> ws_brec(kWsMaxPairs + 1, make_int4(0, 0, 0, 0));
+    std::vector<float> ws_wt;
+    if (pl->n_bins == kBins) {
+        // filterbank of k_fe_pass_a_ws (see WsMelParam): band b = rising slope over interval b (ms.w[k].x) +
+        // falling slope over interval b+1 (ms.w[k].y); warps get contiguous band ranges balanced by cost and walk
+        // them two bands at a time, both zero padded to the same number of float4 blocks
+        const int nm = p->n_mels;
+        auto blocks_of = [&](int bnd) { return (ms.istart[bnd + 2] - ms.istart[bnd] + 3) / 4; };
+        auto weight_of = [&](int bnd, int q) -> float {
+            const int k = ms.istart[bnd] + q;
+            return k < ms.istart[bnd + 1] ? ms.w[k].x : (k < ms.istart[bnd + 2] ? ms.w[k].y : 0.f);
+        };
+        std::vector<double> cost(nm);
+        double total = 0;
+        for (int bnd = 0; bnd < nm; ++bnd) { cost[bnd] = 9.0 * blocks_of(bnd) + 8.0; total += cost[bnd]; }
+        WsMelParam& wm = pl->ws_mel;
+        wm.n_mels = nm;
+        wm.chunk[0] = 0;
+        double run = 0; int c = 1;
+        for (int i = 0; i < nm && c < kWsEpiWarps; ++i) {
+            run += cost[i];
+            if (run >= total * c / kWsEpiWarps) wm.chunk[c++] = i + 1;
+        }
+        for (; c <= kWsEpiWarps; ++c) wm.chunk[c] = nm;
+        int n_pairs = 0;
+        for (int w = 0; w < kWsEpiWarps; ++w) {
+            wm.pair0[w] = n_pairs;
+            for (int bnd = wm.chunk[w]; bnd < wm.chunk[w + 1]; bnd += 2) {
+                const bool has_b = bnd + 1 < wm.chunk[w + 1];
+                const int nb = std::max(blocks_of(bnd), has_b ? blocks_of(bnd + 1) : 0);
+                ws_brec[n_pairs++] = make_int4(ms.istart[bnd], has_b ? ms.istart[bnd + 1] : ms.istart[bnd], nb, (int)ws_wt.size() / 4);
+                for (int blk = 0; blk < nb; ++blk) {
+                    for (int q = 0; q < 4; ++q) ws_wt.push_back(weight_of(bnd, 4 * blk + q));
+                    for (int q = 0; q < 4; ++q) ws_wt.push_back(has_b ? weight_of(bnd + 1, 4 * blk + q) : 0.f);
+                }
+            }
+        }
+        wm.pair0[kWsEpiWarps] = n_pairs;
+        wm.n_taps = (int)ws_wt.size();
+        if (wm.n_taps > kWsMaxTaps || n_pairs > kWsMaxPairs) pl->use_ws = false;   // not reachable for 201 bins and <= 128 bands
+    }
+    if (ws_wt.empty()) ws_wt.push_back(0.f);
+    if (const char* e = getenv("SC_FE_WS")) pl->use_ws = pl->use_ws && atoi(e) != 0;
     // librosa.filters.dct (audio_lib.py:176): row 0 = 1/sqrt(N), row q = sqrt(2/N) cos(q (2n+1) pi / 2N),
     // split into even / odd rows over the first half of the inputs (see k_fe_pass_b)
     const FbLayout fbl = fb_layout(p->n_mels, p->n_mfcc);
@@ -303,7 +351,7 @@ extern "C" int sc_plan_create(const sc_params* p, sc_plan** out) {
     const size_t o_wn = b.add(wn), o_feh = b.add(fe_half), o_glh = b.add(gl_half), o_gli = b.add(gl_inv);
     const size_t o_sq = b.add(gl_sq), o_wss = b.add(inv_wss), o_mw = b.add(ms.w), o_mi = b.add(ms.istart);
     const size_t o_mc = b.add(ms.chunk), o_dcte = b.add(dct_e), o_dcto = b.add(dct_o), o_few = b.add(pl->fe_window), o_glw = b.add(gl_w);
-    const size_t o_wnd = b.add(wn_d), o_fehd = b.add(fe_half_d);
+    const size_t o_wnd = b.add(wn_d), o_fehd = b.add(fe_half_d), o_wsrec = b.add(ws_brec), o_wswt = b.add(ws_wt);
     std::vector<float> zeros(pl->n_bins, 0.f);
     const size_t o_zero = b.add(zeros);
     if (pl->tables.ensure(b.bytes.size())) { delete pl; return SC_ERR_CUDA; }
@@ -328,6 +376,8 @@ extern "C" int sc_plan_create(const sc_params* p, sc_plan** out) {
     pl->mel_chunk = (const int32_t*)(base + o_mc);
     pl->dct_e = (const float*)(base + o_dcte);
     pl->dct_o = (const float*)(base + o_dcto);
+    pl->ws_brec = (const int4*)(base + o_wsrec);
+    pl->ws_wt = (const float*)(base + o_wswt);
     pl->g_fe_win = (const double*)(base + o_few);
     pl->g_gl_win = (const float*)(base + o_glw);
     *out = pl;
@@ -391,6 +441,7 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
     std::vector<int64_t> heap_off(n + 1);
     int64_t total_frames_span = 0;
     constexpr int kPU = 8;                         // units per CTA of the fast pass-A kernels (16 frames per tile)
+    const bool ws = pl->fast && pl->use_ws;        // long utterances: warp-specialised kernel, 24-frame tiles
     const int a_frames = pl->fast ? 2 * kPU : kGenFeFrames;
     for (int u = 0; u < n; ++u) {
         const int64_t T = 1 + slen[u] / hop;
@@ -406,14 +457,18 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
         // first / last tiles gather their reflect padding); shorter utterances, whose padding could wrap more
         // than once, use the plain kernel
         int64_t n_tiles_u = (fcnt[u] + a_frames - 1) / a_frames, k_lo = 0, k_hi = -1;
+        int64_t n_int = 0;
         if (pl->fast) {
-            const int64_t span = (int64_t)kHop * (a_frames - 1) + kNfft;
-            if (slen[u] >= 2 * span + 16) k_hi = n_tiles_u - 1;
+            const int p_frames = ws ? kWsFrames : a_frames;                   // tile of the persistent kernel
+            const int64_t span = (int64_t)kHop * (p_frames - 1) + kNfft;
+            if (slen[u] >= 2 * span + 16) {
+                k_hi = n_tiles_u - 1;
+                n_int = ws ? (fcnt[u] + kWsFrames - 1) / kWsFrames : n_tiles_u;
+            }
         }
-        const int64_t n_int = k_hi >= k_lo ? k_hi - k_lo + 1 : 0;
-        ifirst[u] = (int32_t)k_lo; icount[u] = (int32_t)n_int;
+        ifirst[u] = (int32_t)k_lo; icount[u] = (int32_t)(k_hi >= k_lo ? k_hi - k_lo + 1 : 0);
         pre_int[u + 1] = (int32_t)(pre_int[u] + n_int);
-        const int64_t tb = pre_a[u] + n_tiles_u - n_int;                      // edge (or all generic-path) tiles
+        const int64_t tb = pre_a[u] + n_tiles_u - icount[u];                  // edge (or all generic-path) tiles
         const int64_t tc = pre_b[u] + (fcnt[u] + kFbFrames - 1) / kFbFrames;
         if (ta > INT32_MAX || tb > INT32_MAX) return fail(SC_ERR_INVALID, "sc_frontend_batch: batch too large");
         pre_abs[u + 1] = (int32_t)ta; pre_a[u + 1] = (int32_t)tb; pre_b[u + 1] = (int32_t)tc;
@@ -428,7 +483,8 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
     const size_t w_stat = 0;
     const size_t w_part = (sizeof(UttStat) * n + 255) & ~size_t(255);
     const size_t w_mel = (w_part + sizeof(float) * (size_t)heap_off[n] + 255) & ~size_t(255);
-    const size_t w_end = w_mel + sizeof(float) * (size_t)total_frames_span * pl->prm.n_mels;
+    const size_t w_tiles = (w_mel + sizeof(float) * (size_t)total_frames_span * pl->prm.n_mels + 255) & ~size_t(255);
+    const size_t w_end = w_tiles + (ws ? sizeof(WsTile) * (size_t)pre_int[n] : 0);
     if (int rc = pl->work.ensure(w_end)) return rc;
     unsigned char* wb = static_cast<unsigned char*>(pl->work.p);
     UttStat* stat = reinterpret_cast<UttStat*>(wb + w_stat);
@@ -468,8 +524,31 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
         }
         const size_t mel_bytes = sizeof(float) * 2 * kPU * (pl->prm.n_mels + 1);
         rg.int_first = at<int32_t>(pl, o_if); rg.int_count = at<int32_t>(pl, o_ic);
-        // persistent, warp-specialised, cp.async ring
-        if (pre_int[n] > 0) {
+        if (ws && pre_int[n] > 0) {
+            // warp-specialised persistent kernel (fe_ws.cuh): one CTA per SM
+            static bool ws_attr = false;
+            const size_t mel_s_bytes = sizeof(float) * 2 * kWsFrames * (pl->prm.n_mels | 1);
+            if (!ws_attr) {
+                SC_CUDA(cudaFuncSetAttribute(k_fe_pass_a_ws<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(sizeof(WsSmem<float>) + sizeof(float) * 2 * kWsFrames * (kMaxMels | 1))));
+                SC_CUDA(cudaFuncSetAttribute(k_fe_pass_a_ws<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(sizeof(WsSmem<double>) + sizeof(float) * 2 * kWsFrames * (kMaxMels | 1))));
+                ws_attr = true;
+            }
+            WsTile* tiles = reinterpret_cast<WsTile*>(wb + w_tiles);
+            rg.tile_prefix = at<int32_t>(pl, o_pint);
+            k_ws_tiles<<<(pre_int[n] + 255) / 256, 256, 0, st>>>(rg, pre_int[n], tiles);
+            SC_LAUNCHED();
+            const int grid = pre_int[n] < n_sm ? pre_int[n] : n_sm;
+            if (pl->fp32_fft)
+                k_fe_pass_a_ws<float><<<grid, kWsThreads, sizeof(WsSmem<float>) + mel_s_bytes, st>>>(
+                    wav, tiles, pre_int[n], tb, fp, stat, pdb, mel_raw, pl->ws_brec, pl->ws_wt, pl->ws_mel);
+            else
+                k_fe_pass_a_ws<double><<<grid, kWsThreads, sizeof(WsSmem<double>) + mel_s_bytes, st>>>(
+                    wav, tiles, pre_int[n], tb, fp, stat, pdb, mel_raw, pl->ws_brec, pl->ws_wt, pl->ws_mel);
+            SC_LAUNCHED();
+        } else if (pre_int[n] > 0) {
+            // persistent, warp-specialised, cp.async ring
             rg.tile_prefix = at<int32_t>(pl, o_pint);
             const int per_sm = pl->fp32_fft ? 3 : 2;
             const int grid = pre_int[n] < n_sm * per_sm ? pre_int[n] : n_sm * per_sm;
