@@ -137,6 +137,91 @@ __global__ void __launch_bounds__(kAbsThreads) k_abs_pairwise(const float* __res
     if (tid == 0) heap[heap_off[u] + (1 << D) + idx] = hv[1];
 }
 
+// Second form of the leaf pass: no shared-memory heap and one barrier.  Every 8-lane group derives the bounds of
+// "its" depth-7 slot arithmetically (the tree depends only on n), sums the leaf exactly like NumPy's unrolled
+// block, and writes one of 128 slot values; a node that is already a leaf above depth 7 is owned by its first
+// slot and the other slots hold +0, so folding the 128 slots as a perfect binary tree reproduces NumPy's order
+// (x + 0 = x exactly for the non-negative sums).  (u, subtree index) of a CTA come from a host-built table.
+constexpr int kAbs2Threads = 512;
+__global__ void __launch_bounds__(kAbs2Threads) k_abs_pairwise2(const float* __restrict__ wav, Ragged rg,
+                                                                const int2* __restrict__ recs,
+                                                                const int64_t* __restrict__ heap_off,
+                                                                float* __restrict__ heap) {
+    __shared__ __align__(16) float hv[128];
+    const int tid = threadIdx.x;
+    const int2 rec = __ldg(recs + blockIdx.x);
+    const int u = rec.x, idx = rec.y;
+    const int64_t len = rg.sample_len[u];
+    const int D = abs_depth(len);
+    int64_t start = 0, n64 = len;
+    for (int b = D - 1; b >= 0; --b) {
+        int64_t n2 = n64 / 2;
+        n2 -= n2 % 8;
+        if ((idx >> b) & 1) { start += n2; n64 -= n2; } else { n64 = n2; }
+    }
+    const float* __restrict__ a = wav + rg.sample_off[u] + start;
+    const int n = (int)n64;
+    const int g = tid >> 3, j = tid & 7;
+    constexpr int kRounds = 128 / (kAbs2Threads / 8);
+    int ls[kRounds], ln[kRounds];
+    bool own[kRounds];
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const int s = g + (kAbs2Threads / 8) * r;
+        int o = 0, m = n;
+        bool first = true;
+#pragma unroll
+        for (int lvl = 6; lvl >= 0; --lvl) {
+            const int bit = (s >> lvl) & 1;
+            if (m > 128) {
+                int n2 = m / 2;
+                n2 -= n2 % 8;
+                if (bit) { o += n2; m -= n2; } else { m = n2; }
+            } else if (bit) {
+                first = false;
+            }
+        }
+        ls[r] = o; ln[r] = m; own[r] = first && m > 0;
+    }
+    // all loads of both rounds first
+    float v[kRounds][16], tl[kRounds][7];
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const float* __restrict__ p = a + ls[r];
+        const int m = own[r] ? ln[r] : 0;
+        const int body = m >= 8 ? m - (m % 8) : 0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[r][q] = 8 * q < body ? __ldg(p + 8 * q + j) : 0.f;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) tl[r][q] = body + q < m ? __ldg(p + body + q) : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const int m = own[r] ? ln[r] : 0;
+        const int body = m >= 8 ? m - (m % 8) : 0;
+        float acc = fabsf(v[r][0]);
+#pragma unroll
+        for (int q = 1; q < 16; ++q)
+            if (8 * q < body) acc += fabsf(v[r][q]);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        float res = body > 0 ? acc : 0.f;                  // m < 8: plain left-to-right sum of the tail
+#pragma unroll
+        for (int q = 0; q < 7; ++q)
+            if (body + q < m) res += fabsf(tl[r][q]);
+        if (j == 0) hv[g + (kAbs2Threads / 8) * r] = res;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        const float4 x = reinterpret_cast<const float4*>(hv)[tid];
+        float t = (x.x + x.y) + (x.z + x.w);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (tid == 0) heap[heap_off[u] + (1 << D) + idx] = t;
+    }
+}
+
 __global__ void __launch_bounds__(128) k_gain_finalize(Ragged rg, const int64_t* __restrict__ heap_off,
                                                        float* __restrict__ heap, UttStat* __restrict__ stat,
                                                        double mean_abs_amp_norm, int use_gain,
@@ -758,6 +843,415 @@ k_fe_pass_b(Ragged rg, FeTables tb, FeParams prm, const UttStat* __restrict__ st
                 dst[r * width + q] = fminf(fmaxf(v, -cl), cl);
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MFCC[0, 0] of every utterance (audio_lib.py:221), one thread per utterance, written to stat[u].pad[0].
+// Same clip, same (x[n] + x[N-1-n]) folding and same FMA order as coefficient 0 of the DCT in pass B, so that
+// MFCC[0, 0] - MFCC[0, 0] is exactly 0 like the reference's.
+__global__ void __launch_bounds__(128) k_fe_c00(Ragged rg, FeTables tb, FeParams prm, UttStat* __restrict__ stat,
+                                                const float* __restrict__ mel_raw) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= rg.n_utts) return;
+    float a = 0.f;
+    if (prm.norm_first) {
+        const int n_mels = tb.n_mels;
+        const FbLayout L = fb_layout(n_mels, tb.n_mfcc);
+        const float m_floor = 2.0f * db10(fmaxf(__uint_as_float(stat[u].m_max), 1e-5f)) - 80.0f;
+        const float* __restrict__ src = mel_raw + rg.frame_off[u] * n_mels;
+        const int pairs = n_mels / 2;
+        for (int n = 0; n < L.half; ++n) {
+            const float x1 = fmaxf(__ldg(src + n), m_floor);
+            const float x2 = n < pairs ? fmaxf(__ldg(src + (n_mels - 1 - n)), m_floor) : 0.f;
+            a = fmaf(__ldg(tb.dct_e + n * L.ne_pad), n < pairs ? x1 + x2 : x1, a);
+        }
+    }
+    stat[u].pad[0] = a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass B, vector form (n_mels % 8 == 0, n_mfcc % 4 == 0, 16-byte aligned buffers).  One CTA = kFbFrames
+// consecutive frames of one utterance.  Same arithmetic as k_fe_pass_b, but every global access is a 128-bit
+// one issued before its first use, the mel rows are folded into (x[n] + x[N-1-n], x[n] - x[N-1-n]) by the
+// thread that loads both halves, and MFCC[0, 0] comes from k_fe_c00 instead of being recomputed by every CTA.
+struct Fb2Layout {
+    int half, ne_pad, sd_ld, cc_ld;
+    size_t off_e, off_o, off_sd, off_cc, bytes;
+};
+__host__ __device__ inline Fb2Layout fb2_layout(int n_mels, int n_mfcc) {
+    Fb2Layout L;
+    L.half = n_mels / 2;
+    L.ne_pad = (((n_mfcc + 1) / 2) + 3) & ~3;
+    L.sd_ld = L.half | 1;                           // float2 stride, odd => conflict-free for lane = row
+    L.cc_ld = 2 * L.ne_pad + 4;                     // = 4 (mod 8) floats: 128-bit row accesses with lane = row are conflict-free
+    size_t o = 0;
+    L.off_e = o;  o += sizeof(float) * L.half * L.ne_pad;
+    L.off_o = o;  o += sizeof(float) * L.half * L.ne_pad;
+    L.off_sd = o; o += sizeof(float2) * (kFbFrames + 2) * L.sd_ld;
+    o = (o + 15) & ~size_t(15);
+    L.off_cc = o; o += sizeof(float) * (kFbFrames + 2) * L.cc_ld;
+    L.bytes = o;
+    return L;
+}
+
+__device__ __forceinline__ float4 fb2_norm(float4 x, float sub, float mul, float cl) {
+    x.x = fminf(fmaxf(mul * (x.x - sub), -cl), cl);
+    x.y = fminf(fmaxf(mul * (x.y - sub), -cl), cl);
+    x.z = fminf(fmaxf(mul * (x.z - sub), -cl), cl);
+    x.w = fminf(fmaxf(mul * (x.w - sub), -cl), cl);
+    return x;
+}
+
+__global__ void __launch_bounds__(kFbThreads, 4)
+k_fe_pass_b2(Ragged rg, FeTables tb, FeParams prm, const UttStat* __restrict__ stat,
+             const float* __restrict__ mel_raw, float* __restrict__ pdb, float* __restrict__ mel_out,
+             float* __restrict__ mfcc_out, int n_bins) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int u = find_utt(rg.tile_prefix, rg.n_utts, tile);
+    const int t0 = (tile - rg.tile_prefix[u]) * kFbFrames;
+    const int T = rg.frame_cnt[u];
+    const int nfr = min(kFbFrames, T - t0);
+    const UttStat st = stat[u];
+    const int n_mels = tb.n_mels, n_mfcc = tb.n_mfcc;
+    const Fb2Layout L = fb2_layout(n_mels, n_mfcc);
+    float* dct_e = reinterpret_cast<float*>(smem_raw + L.off_e);      // [half][ne_pad]
+    float* dct_o = reinterpret_cast<float*>(smem_raw + L.off_o);      // [half][ne_pad]
+    float2* sd_s = reinterpret_cast<float2*>(smem_raw + L.off_sd);    // [rows][sd_ld] (s, d)
+    float* cc_s = reinterpret_cast<float*>(smem_raw + L.off_cc);      // [rows][cc_ld] scaled cepstra
+    const float cl = prm.clip ? 1.0f : __int_as_float(0x7f800000);
+    const int64_t row0 = rg.frame_off[u] + t0;
+
+    // ---- every global load of the tile is issued before the first use: one DRAM latency per CTA
+    constexpr int kPdbIt = (kFbFrames * kBins / 4 + kFbThreads - 1) / kFbThreads;
+    float4* __restrict__ p4 = reinterpret_cast<float4*>(pdb + row0 * n_bins);
+    const int n_pdb = nfr * n_bins;
+    const int n4 = n_bins == kBins ? n_pdb >> 2 : 0;          // other bin counts take the plain loop below
+    float4 pv[kPdbIt];
+#pragma unroll
+    for (int it = 0; it < kPdbIt; ++it) {
+        const int e = tid + it * kFbThreads;
+        if (e < n4) pv[it] = p4[e];
+    }
+
+    // ---- mel dB rows t0-1 .. t0+nfr (halo for the delta): clip (:172), normalised rows out (:235, :240), fold
+    {
+        const float m_hi = 2.0f * db10(fmaxf(__uint_as_float(st.m_max), 1e-5f));
+        const float m_floor = m_hi - 80.0f;
+        const float m_lo = fmaxf(2.0f * db10(fmaxf(__uint_as_float(st.m_min), 1e-5f)), m_floor);
+        const float sub = prm.shift_m ? m_lo : 0.0f;
+        const float mul = prm.shift_m ? prm.m_db_norm_factor : 1.0f;
+        const float4* __restrict__ src = reinterpret_cast<const float4*>(mel_raw + rg.frame_off[u] * n_mels);
+        float4* __restrict__ dst = reinterpret_cast<float4*>(mel_out + rg.frame_off[u] * n_mels);
+        const int q_row = n_mels / 8;                 // tasks per row: float4 m and its mirror
+        const int row4 = n_mels / 4;
+        const int n_task = (nfr + 2) * q_row;
+        constexpr int kMaxIt = ((kFbFrames + 2) * (kMaxMels / 8) + kFbThreads - 1) / kFbThreads;
+        float4 a[kMaxIt], b[kMaxIt];
+#pragma unroll
+        for (int it = 0; it < kMaxIt; ++it) {
+            const int task = tid + it * kFbThreads;
+            const int r = task / q_row, m4 = task - r * q_row;
+            const int t = t0 - 1 + r;
+            if (task < n_task && t >= 0 && t < T) {
+                a[it] = __ldg(src + (int64_t)t * row4 + m4);
+                b[it] = __ldg(src + (int64_t)t * row4 + (row4 - 1 - m4));
+            }
+        }
+        for (int e = tid; e < L.half * L.ne_pad; e += kFbThreads) { dct_e[e] = tb.dct_e[e]; dct_o[e] = tb.dct_o[e]; }
+#pragma unroll
+        for (int it = 0; it < kMaxIt; ++it) {
+            const int task = tid + it * kFbThreads;
+            if (task >= n_task) break;
+            const int r = task / q_row, m4 = task - r * q_row;
+            const int t = t0 - 1 + r;
+            float2* __restrict__ sd = sd_s + r * L.sd_ld + 4 * m4;
+            if (t >= 0 && t < T) {
+                float4 xa = a[it], xb = b[it];
+                xa.x = fmaxf(xa.x, m_floor); xa.y = fmaxf(xa.y, m_floor); xa.z = fmaxf(xa.z, m_floor); xa.w = fmaxf(xa.w, m_floor);
+                xb.x = fmaxf(xb.x, m_floor); xb.y = fmaxf(xb.y, m_floor); xb.z = fmaxf(xb.z, m_floor); xb.w = fmaxf(xb.w, m_floor);
+                if (r >= 1 && r <= nfr) {
+                    dst[(int64_t)t * row4 + m4] = fb2_norm(xa, sub, mul, cl);
+                    dst[(int64_t)t * row4 + (row4 - 1 - m4)] = fb2_norm(xb, sub, mul, cl);
+                }
+                sd[0] = make_float2(xa.x + xb.w, xa.x - xb.w);
+                sd[1] = make_float2(xa.y + xb.z, xa.y - xb.z);
+                sd[2] = make_float2(xa.z + xb.y, xa.z - xb.y);
+                sd[3] = make_float2(xa.w + xb.x, xa.w - xb.x);
+            } else {
+                sd[0] = sd[1] = sd[2] = sd[3] = make_float2(0.f, 0.f);
+            }
+        }
+    }
+
+    // ---- power dB, in place: top_db clip (:157), min shift + scale (:231), clip (:239)
+    {
+        const float hi = db10(fmaxf(__uint_as_float(st.p_max), 1e-10f));
+        const float floor_db = hi - 80.0f;
+        const float lo = fmaxf(db10(fmaxf(__uint_as_float(st.p_min), 1e-10f)), floor_db);
+        const float sub = prm.shift_p ? lo : 0.0f;
+        const float mul = prm.shift_p ? prm.p_db_norm_factor : 1.0f;
+        auto fix = [&](float4 v) {
+            v.x = fmaxf(v.x, floor_db); v.y = fmaxf(v.y, floor_db); v.z = fmaxf(v.z, floor_db); v.w = fmaxf(v.w, floor_db);
+            return fb2_norm(v, sub, mul, cl);
+        };
+#pragma unroll
+        for (int it = 0; it < kPdbIt; ++it) {
+            const int e = tid + it * kFbThreads;
+            if (e < n4) p4[e] = fix(pv[it]);
+        }
+        float* __restrict__ p = pdb + row0 * n_bins;
+        for (int q = (n4 << 2) + tid; q < n_pdb; q += kFbThreads)
+            p[q] = fminf(fmaxf(mul * (fmaxf(p[q], floor_db) - sub), -cl), cl);
+    }
+    __syncthreads();
+
+    // ---- DCT-II (:176-179) on the folded rows: task = (row, 4 even + 4 odd coefficients); lanes = consecutive rows
+    {
+        const int groups = L.ne_pad >> 2;
+        const int rows = nfr + 2;
+        const float c00 = st.pad[0];
+        const float sc = prm.mfcc_norm_factor;
+        const int ld4 = L.ne_pad >> 2;
+        for (int task = tid; task < rows * groups; task += kFbThreads) {
+            const int g = task / rows;
+            const int r = task - g * rows;
+            const float2* __restrict__ x = sd_s + r * L.sd_ld;
+            const float4* __restrict__ e4 = reinterpret_cast<const float4*>(dct_e) + g;
+            const float4* __restrict__ o4 = reinterpret_cast<const float4*>(dct_o) + g;
+            float ae0 = 0.f, ae1 = 0.f, ae2 = 0.f, ae3 = 0.f, ao0 = 0.f, ao1 = 0.f, ao2 = 0.f, ao3 = 0.f;
+#pragma unroll 8
+            for (int n = 0; n < L.half; ++n) {
+                const float2 v = x[n];
+                const float4 e = e4[n * ld4], o = o4[n * ld4];
+                ae0 = fmaf(e.x, v.x, ae0); ae1 = fmaf(e.y, v.x, ae1); ae2 = fmaf(e.z, v.x, ae2); ae3 = fmaf(e.w, v.x, ae3);
+                ao0 = fmaf(o.x, v.y, ao0); ao1 = fmaf(o.y, v.y, ao1); ao2 = fmaf(o.z, v.y, ao2); ao3 = fmaf(o.w, v.y, ao3);
+            }
+            if (g == 0) ae0 -= c00;
+            float4* __restrict__ c = reinterpret_cast<float4*>(cc_s + r * L.cc_ld + 8 * g);
+            c[0] = make_float4(sc * ae0, sc * ao0, sc * ae1, sc * ao1);
+            c[1] = make_float4(sc * ae2, sc * ao2, sc * ae3, sc * ao3);
+        }
+    }
+    __syncthreads();
+    // ---- MFCC (+ delta, :226-228) output, clip (:238)
+    {
+        const int q_row = n_mfcc / 4;
+        const int width4 = (prm.use_delta ? 2 * n_mfcc : n_mfcc) / 4;
+        float4* __restrict__ dst = reinterpret_cast<float4*>(mfcc_out) + row0 * width4;
+        for (int task = tid; task < nfr * q_row; task += kFbThreads) {
+            const int r = task / q_row, q4 = task - r * q_row;
+            const int t = t0 + r;
+            const float4 c = *reinterpret_cast<const float4*>(cc_s + (r + 1) * L.cc_ld + 4 * q4);
+            dst[r * width4 + q4] = make_float4(fminf(fmaxf(c.x, -cl), cl), fminf(fmaxf(c.y, -cl), cl),
+                                               fminf(fmaxf(c.z, -cl), cl), fminf(fmaxf(c.w, -cl), cl));
+            if (prm.use_delta) {
+                float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t != 0 && t != T - 1) {
+                    const float4 up = *reinterpret_cast<const float4*>(cc_s + (r + 2) * L.cc_ld + 4 * q4);
+                    const float4 dn = *reinterpret_cast<const float4*>(cc_s + r * L.cc_ld + 4 * q4);
+                    d = make_float4(fminf(fmaxf(2.0f * (up.x - dn.x), -cl), cl), fminf(fmaxf(2.0f * (up.y - dn.y), -cl), cl),
+                                    fminf(fmaxf(2.0f * (up.z - dn.z), -cl), cl), fminf(fmaxf(2.0f * (up.w - dn.w), -cl), cl));
+                }
+                dst[r * width4 + q_row + q4] = d;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass B specialised at compile time for the hp/*.json feature sizes (80 mels, 40 MFCC, 201 bins).
+// On top of k_fe_pass_b2: the DCT basis lives in the kernel-parameter constant bank and the n loop is fully
+// unrolled, so every multiply-add takes its weight as an immediate constant operand (no per-CTA table copy,
+// no weight loads); one warp per coefficient group with lane = row (28 frames + 2 halo rows = 30 lanes);
+// tiles come from a precomputed table instead of a binary search per CTA.
+constexpr int kB3Frames = 28;                       // multiple of 4: 16-byte aligned power-dB tiles
+constexpr int kB3Rows = kB3Frames + 2;
+constexpr int kB3Mels = 80, kB3Mfcc = 40, kB3Half = kB3Mels / 2, kB3Groups = kB3Mfcc / 8;
+constexpr int kB3Threads = 32 * kB3Groups;          // 160
+constexpr int kB3SdLd = kB3Half | 1;                // float2 stride
+constexpr int kB3CcLd = kB3Mfcc + 4;                // 44 floats
+
+struct B3Tile {
+    int64_t frame_off;      // first row of the utterance
+    int32_t u, t0, T, pad;
+};
+
+__global__ void k_b3_tiles(Ragged rg, int total_tiles, B3Tile* __restrict__ out) {
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= total_tiles) return;
+    const int u = find_utt(rg.tile_prefix, rg.n_utts, tile);
+    B3Tile t;
+    t.u = u;
+    t.t0 = (tile - rg.tile_prefix[u]) * kB3Frames;
+    t.T = rg.frame_cnt[u];
+    t.frame_off = rg.frame_off[u];
+    t.pad = 0;
+    out[tile] = t;
+}
+
+// One (row, coefficient group) DCT task: 4 even + 4 odd coefficients, weights as broadcast 128-bit shared loads.
+__device__ __forceinline__ void b3_dct_group(const float4* __restrict__ e4, const float4* __restrict__ o4,
+                                             const float2* __restrict__ x, bool first_group, float c00, float sc,
+                                             float* __restrict__ out) {
+    float ae0 = 0.f, ae1 = 0.f, ae2 = 0.f, ae3 = 0.f, ao0 = 0.f, ao1 = 0.f, ao2 = 0.f, ao3 = 0.f;
+#pragma unroll 8
+    for (int n = 0; n < kB3Half; ++n) {
+        const float2 v = x[n];
+        const float4 e = e4[n * kB3Groups], o = o4[n * kB3Groups];
+        ae0 = fmaf(e.x, v.x, ae0); ae1 = fmaf(e.y, v.x, ae1); ae2 = fmaf(e.z, v.x, ae2); ae3 = fmaf(e.w, v.x, ae3);
+        ao0 = fmaf(o.x, v.y, ao0); ao1 = fmaf(o.y, v.y, ao1); ao2 = fmaf(o.z, v.y, ao2); ao3 = fmaf(o.w, v.y, ao3);
+    }
+    if (first_group) ae0 -= c00;
+    float4* __restrict__ c = reinterpret_cast<float4*>(out);
+    c[0] = make_float4(sc * ae0, sc * ao0, sc * ae1, sc * ao1);
+    c[1] = make_float4(sc * ae2, sc * ao2, sc * ae3, sc * ao3);
+}
+
+// Persistent: a CTA keeps the DCT basis in shared memory for its whole life and loads tile i+1 into registers
+// while the DCT and the MFCC output of tile i run, so DRAM latency is hidden behind arithmetic.
+__global__ void __launch_bounds__(kB3Threads, 3)
+k_fe_pass_b3(const B3Tile* __restrict__ tiles, int total_tiles, FeTables tb, FeParams prm, const UttStat* __restrict__ stat,
+             const float* __restrict__ mel_raw, float* __restrict__ pdb, float* __restrict__ mel_out,
+             float* __restrict__ mfcc_out) {
+    __shared__ __align__(16) float dct_e[kB3Half * (kB3Mfcc / 2)];   // [n][q/2]
+    __shared__ __align__(16) float dct_o[kB3Half * (kB3Mfcc / 2)];
+    __shared__ __align__(16) float2 sd_s[kB3Rows * kB3SdLd];      // (x[n] + x[79-n], x[n] - x[79-n])
+    __shared__ __align__(16) float cc_s[kB3Rows * kB3CcLd];       // scaled cepstra
+    const int tid = threadIdx.x;
+    const float cl = prm.clip ? 1.0f : __int_as_float(0x7f800000);
+    constexpr int kPdbIt = (kB3Frames * kBins / 4 + kB3Threads - 1) / kB3Threads;       // 9
+    constexpr int kMelIt = (kB3Rows * (kB3Mels / 8) + kB3Threads - 1) / kB3Threads;     // 2
+    constexpr int kQRow = kB3Mels / 8, kRow4 = kB3Mels / 4;
+    for (int e = tid; e < kB3Half * (kB3Mfcc / 2); e += kB3Threads) { dct_e[e] = tb.dct_e[e]; dct_o[e] = tb.dct_o[e]; }
+
+    float4 pv[kPdbIt], a[kMelIt], b[kMelIt];
+    B3Tile tl;
+    UttStat st;
+    // load(): descriptor + every global load of a tile, issued back to back
+    auto load = [&](int tile) {
+        tl = tiles[tile];
+        st = stat[tl.u];
+        const int nfr = min(kB3Frames, tl.T - tl.t0);
+        const float4* __restrict__ p4 = reinterpret_cast<const float4*>(pdb + (tl.frame_off + tl.t0) * kBins);
+        const int n4 = (nfr * kBins) >> 2;
+#pragma unroll
+        for (int it = 0; it < kPdbIt; ++it) {
+            const int e = tid + it * kB3Threads;
+            if (e < n4) pv[it] = p4[e];
+        }
+        const float4* __restrict__ msrc = reinterpret_cast<const float4*>(mel_raw + tl.frame_off * kB3Mels);
+#pragma unroll
+        for (int it = 0; it < kMelIt; ++it) {
+            const int task = tid + it * kB3Threads;
+            const int r = task / kQRow, m4 = task - r * kQRow;
+            const int t = tl.t0 - 1 + r;
+            if (r < nfr + 2 && t >= 0 && t < tl.T) {
+                a[it] = __ldg(msrc + (int64_t)t * kRow4 + m4);
+                b[it] = __ldg(msrc + (int64_t)t * kRow4 + (kRow4 - 1 - m4));
+            }
+        }
+    };
+    int tile = blockIdx.x;
+    if (tile < total_tiles) load(tile);
+    for (; tile < total_tiles; tile += gridDim.x) {
+        const int t0 = tl.t0, T = tl.T;
+        const int nfr = min(kB3Frames, T - t0);
+        const int64_t row0 = tl.frame_off + t0;
+        const int64_t frame_off = tl.frame_off;
+        const float c00 = st.pad[0];
+        // ---- mel dB rows t0-1 .. t0+nfr (halo for the delta): clip (:172), normalised rows out (:235, :240), fold
+        {
+            const float m_hi = 2.0f * db10(fmaxf(__uint_as_float(st.m_max), 1e-5f));
+            const float m_floor = m_hi - 80.0f;
+            const float m_lo = fmaxf(2.0f * db10(fmaxf(__uint_as_float(st.m_min), 1e-5f)), m_floor);
+            const float sub = prm.shift_m ? m_lo : 0.0f;
+            const float mul = prm.shift_m ? prm.m_db_norm_factor : 1.0f;
+            float4* __restrict__ dst = reinterpret_cast<float4*>(mel_out + frame_off * kB3Mels);
+#pragma unroll
+            for (int it = 0; it < kMelIt; ++it) {
+                const int task = tid + it * kB3Threads;
+                const int r = task / kQRow, m4 = task - r * kQRow;
+                const int t = t0 - 1 + r;
+                if (r >= kB3Rows) break;
+                float2* __restrict__ sd = sd_s + r * kB3SdLd + 4 * m4;
+                if (r < nfr + 2 && t >= 0 && t < T) {
+                    float4 xa = a[it], xb = b[it];
+                    xa.x = fmaxf(xa.x, m_floor); xa.y = fmaxf(xa.y, m_floor); xa.z = fmaxf(xa.z, m_floor); xa.w = fmaxf(xa.w, m_floor);
+                    xb.x = fmaxf(xb.x, m_floor); xb.y = fmaxf(xb.y, m_floor); xb.z = fmaxf(xb.z, m_floor); xb.w = fmaxf(xb.w, m_floor);
+                    if (r >= 1 && r <= nfr) {
+                        dst[(int64_t)t * kRow4 + m4] = fb2_norm(xa, sub, mul, cl);
+                        dst[(int64_t)t * kRow4 + (kRow4 - 1 - m4)] = fb2_norm(xb, sub, mul, cl);
+                    }
+                    sd[0] = make_float2(xa.x + xb.w, xa.x - xb.w);
+                    sd[1] = make_float2(xa.y + xb.z, xa.y - xb.z);
+                    sd[2] = make_float2(xa.z + xb.y, xa.z - xb.y);
+                    sd[3] = make_float2(xa.w + xb.x, xa.w - xb.x);
+                } else {
+                    sd[0] = sd[1] = sd[2] = sd[3] = make_float2(0.f, 0.f);
+                }
+            }
+        }
+        // ---- power dB, in place: top_db clip (:157), min shift + scale (:231), clip (:239)
+        {
+            const float hi = db10(fmaxf(__uint_as_float(st.p_max), 1e-10f));
+            const float floor_db = hi - 80.0f;
+            const float lo = fmaxf(db10(fmaxf(__uint_as_float(st.p_min), 1e-10f)), floor_db);
+            const float sub = prm.shift_p ? lo : 0.0f;
+            const float mul = prm.shift_p ? prm.p_db_norm_factor : 1.0f;
+            float4* __restrict__ p4 = reinterpret_cast<float4*>(pdb + row0 * kBins);
+            const int n_pdb = nfr * kBins;
+            const int n4 = n_pdb >> 2;
+#pragma unroll
+            for (int it = 0; it < kPdbIt; ++it) {
+                const int e = tid + it * kB3Threads;
+                if (e < n4) {
+                    float4 v = pv[it];
+                    v.x = fmaxf(v.x, floor_db); v.y = fmaxf(v.y, floor_db); v.z = fmaxf(v.z, floor_db); v.w = fmaxf(v.w, floor_db);
+                    p4[e] = fb2_norm(v, sub, mul, cl);
+                }
+            }
+            float* __restrict__ p = pdb + row0 * kBins;
+            for (int q = (n4 << 2) + tid; q < n_pdb; q += kB3Threads)
+                p[q] = fminf(fmaxf(mul * (fmaxf(p[q], floor_db) - sub), -cl), cl);
+        }
+        __syncthreads();                       // sd_s complete (and the previous tile's cc_s fully read)
+        if (tile + (int)gridDim.x < total_tiles) load(tile + gridDim.x);      // next tile in flight during the DCT
+        // ---- DCT-II (:176-179): warp = coefficient group (4 even + 4 odd), lane = row
+        {
+            const int lane = tid & 31, g = tid >> 5;
+            if (lane < kB3Rows)
+                b3_dct_group(reinterpret_cast<const float4*>(dct_e) + g, reinterpret_cast<const float4*>(dct_o) + g,
+                             sd_s + lane * kB3SdLd, g == 0, c00, prm.mfcc_norm_factor, cc_s + lane * kB3CcLd + 8 * g);
+        }
+        __syncthreads();
+        // ---- MFCC (+ delta, :226-228) output, clip (:238)
+        {
+            constexpr int kQ = kB3Mfcc / 4;
+            const int width4 = (prm.use_delta ? 2 * kB3Mfcc : kB3Mfcc) / 4;
+            float4* __restrict__ dst = reinterpret_cast<float4*>(mfcc_out) + row0 * width4;
+            for (int task = tid; task < nfr * kQ; task += kB3Threads) {
+                const int r = task / kQ, q4 = task - r * kQ;
+                const int t = t0 + r;
+                const float4 c = *reinterpret_cast<const float4*>(cc_s + (r + 1) * kB3CcLd + 4 * q4);
+                dst[r * width4 + q4] = make_float4(fminf(fmaxf(c.x, -cl), cl), fminf(fmaxf(c.y, -cl), cl),
+                                                   fminf(fmaxf(c.z, -cl), cl), fminf(fmaxf(c.w, -cl), cl));
+                if (prm.use_delta) {
+                    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (t != 0 && t != T - 1) {
+                        const float4 up = *reinterpret_cast<const float4*>(cc_s + (r + 2) * kB3CcLd + 4 * q4);
+                        const float4 dn = *reinterpret_cast<const float4*>(cc_s + r * kB3CcLd + 4 * q4);
+                        d = make_float4(fminf(fmaxf(2.0f * (up.x - dn.x), -cl), cl), fminf(fmaxf(2.0f * (up.y - dn.y), -cl), cl),
+                                        fminf(fmaxf(2.0f * (up.z - dn.z), -cl), cl), fminf(fmaxf(2.0f * (up.w - dn.w), -cl), cl));
+                    }
+                    dst[r * width4 + kQ + q4] = d;
+                }
+            }
+        }
+        // the next iteration's first shared-memory writes (sd_s) come after every thread finished the DCT reads of sd_s
+        // (second barrier above); cc_s is next written after the first barrier of the next iteration
     }
 }
 

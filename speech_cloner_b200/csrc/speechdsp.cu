@@ -125,6 +125,8 @@ struct sc_plan {
     WsMelParam ws_mel{};     // band / bin ranges of the epilogue warps of k_fe_pass_a_ws
     const int4* ws_brec = nullptr;  // per-band (first tap, float4 blocks, weight offset)
     const float* ws_wt = nullptr;   // padded filterbank weights
+    bool use_b2 = true;      // vector form of pass B (env SC_FE_B2=0 selects the scalar kernel)
+    bool use_b3 = false;     // compile-time specialised pass B (80 mels, 40 MFCC, 201 bins; env SC_FE_B3=0 disables)
     bool use_ws = true;      // warp-specialised pass A (env SC_FE_WS=0 selects the older persistent kernel)
     int64_t fe_group_frames = int64_t(1) << 60;   // frames per front-end group (env SC_FE_GROUP_FRAMES); measured: grouping for L2 residency only adds launch latency, so off by default
 };
@@ -337,6 +339,7 @@ extern "C" int sc_plan_create(const sc_params* p, sc_plan** out) {
     }
     if (ws_wt.empty()) ws_wt.push_back(0.f);
     if (const char* e = getenv("SC_FE_WS")) pl->use_ws = pl->use_ws && atoi(e) != 0;
+    if (const char* e = getenv("SC_FE_B2")) pl->use_b2 = atoi(e) != 0;
     // librosa.filters.dct (audio_lib.py:176): row 0 = 1/sqrt(N), row q = sqrt(2/N) cos(q (2n+1) pi / 2N),
     // split into even / odd rows over the first half of the inputs (see k_fe_pass_b)
     const FbLayout fbl = fb_layout(p->n_mels, p->n_mfcc);
@@ -348,6 +351,10 @@ extern "C" int sc_plan_create(const sc_params* p, sc_plan** out) {
             if (q & 1) dct_o[(size_t)m * fbl.no_pad + q / 2] = (float)v;
             else dct_e[(size_t)m * fbl.ne_pad + q / 2] = (float)v;
         }
+    if (pl->n_bins == kBins && p->n_mels == kB3Mels && p->n_mfcc == kB3Mfcc) {
+        pl->use_b3 = true;
+        if (const char* e = getenv("SC_FE_B3")) pl->use_b3 = atoi(e) != 0;
+    }
     const size_t o_wn = b.add(wn), o_feh = b.add(fe_half), o_glh = b.add(gl_half), o_gli = b.add(gl_inv);
     const size_t o_sq = b.add(gl_sq), o_wss = b.add(inv_wss), o_mw = b.add(ms.w), o_mi = b.add(ms.istart);
     const size_t o_mc = b.add(ms.chunk), o_dcte = b.add(dct_e), o_dcto = b.add(dct_o), o_few = b.add(pl->fe_window), o_glw = b.add(gl_w);
@@ -432,12 +439,24 @@ static FeParams fe_params(const sc_plan* pl) {
 }
 
 // ------------------------------------------------------------------------------ front-end
+// (utterance, subtree index) of every CTA of k_abs_pairwise2
+static std::vector<int2> abs_recs(const std::vector<int32_t>& pre, int n) {
+    std::vector<int2> r((size_t)pre[n]);
+    for (int u = 0; u < n; ++u)
+        for (int i = pre[u]; i < pre[u + 1]; ++i) r[i] = make_int2(u, i - pre[u]);
+    return r;
+}
+static bool use_abs2() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SC_FE_ABS2"); v = e ? atoi(e) != 0 : 1; }
+    return v != 0;
+}
 // one L2-resident group of utterances [0, n) (pointers already offset by the caller)
 static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, const int64_t* slen_in, int32_t n,
                           float* mfcc, float* mel, float* pdb, const int64_t* foff, cudaStream_t st, int group) {
     const int hop = pl->prm.hop_length;
     std::vector<int64_t> slen(slen_in, slen_in + n), so(soff, soff + n), fo(foff, foff + n);
-    std::vector<int32_t> fcnt(n), pre_abs(n + 1), pre_a(n + 1), pre_b(n + 1), pre_int(n + 1), ifirst(n), icount(n);
+    std::vector<int32_t> fcnt(n), pre_abs(n + 1), pre_a(n + 1), pre_b(n + 1), pre_b3(n + 1), pre_int(n + 1), ifirst(n), icount(n);
     std::vector<int64_t> heap_off(n + 1);
     int64_t total_frames_span = 0;
     constexpr int kPU = 8;                         // units per CTA of the fast pass-A kernels (16 frames per tile)
@@ -448,7 +467,7 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
         fcnt[u] = (int32_t)T;
         if (fo[u] + T > total_frames_span) total_frames_span = fo[u] + T;
     }
-    pre_abs[0] = pre_a[0] = pre_b[0] = pre_int[0] = 0;
+    pre_abs[0] = pre_a[0] = pre_b[0] = pre_b3[0] = pre_int[0] = 0;
     heap_off[0] = 0;
     for (int u = 0; u < n; ++u) {
         const int64_t ta = pre_abs[u] + (int64_t(1) << abs_depth(slen[u]));
@@ -472,11 +491,14 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
         const int64_t tc = pre_b[u] + (fcnt[u] + kFbFrames - 1) / kFbFrames;
         if (ta > INT32_MAX || tb > INT32_MAX) return fail(SC_ERR_INVALID, "sc_frontend_batch: batch too large");
         pre_abs[u + 1] = (int32_t)ta; pre_a[u + 1] = (int32_t)tb; pre_b[u + 1] = (int32_t)tc;
+        pre_b3[u + 1] = pre_b3[u] + (fcnt[u] + kB3Frames - 1) / kB3Frames;
     }
     Blob b;
     const size_t o_so = b.add(so), o_sl = b.add(slen), o_fo = b.add(fo), o_fc = b.add(fcnt);
     const size_t o_pabs = b.add(pre_abs), o_pa = b.add(pre_a), o_pb = b.add(pre_b), o_heap = b.add(heap_off);
     const size_t o_pint = b.add(pre_int), o_if = b.add(ifirst), o_ic = b.add(icount);
+    const size_t o_arec = b.add(abs_recs(pre_abs, n));
+    const size_t o_pb3 = b.add(pre_b3);
     if (int rc = upload_blob(pl, b, st)) return rc;
 
     // workspace: stats | abs partials | raw mel
@@ -484,7 +506,8 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
     const size_t w_part = (sizeof(UttStat) * n + 255) & ~size_t(255);
     const size_t w_mel = (w_part + sizeof(float) * (size_t)heap_off[n] + 255) & ~size_t(255);
     const size_t w_tiles = (w_mel + sizeof(float) * (size_t)total_frames_span * pl->prm.n_mels + 255) & ~size_t(255);
-    const size_t w_end = w_tiles + (ws ? sizeof(WsTile) * (size_t)pre_int[n] : 0);
+    const size_t w_b3 = (w_tiles + (ws ? sizeof(WsTile) * (size_t)pre_int[n] : 0) + 255) & ~size_t(255);
+    const size_t w_end = w_b3 + sizeof(B3Tile) * (size_t)pre_b3[n];
     if (int rc = pl->work.ensure(w_end)) return rc;
     unsigned char* wb = static_cast<unsigned char*>(pl->work.p);
     UttStat* stat = reinterpret_cast<UttStat*>(wb + w_stat);
@@ -502,7 +525,8 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
     if (pl->profile) { if (int rc = prof_event(pl, 4 * group, st)) return rc; pl->pev_kind = 1; pl->pev_groups = group + 1; }
     if (fp.use_gain) {
         rg.tile_prefix = at<int32_t>(pl, o_pabs);
-        k_abs_pairwise<<<pre_abs[n], kAbsThreads, 0, st>>>(wav, rg, at<int64_t>(pl, o_heap), heap);
+        if (use_abs2()) k_abs_pairwise2<<<pre_abs[n], kAbs2Threads, 0, st>>>(wav, rg, at<int2>(pl, o_arec), at<int64_t>(pl, o_heap), heap);
+        else k_abs_pairwise<<<pre_abs[n], kAbsThreads, 0, st>>>(wav, rg, at<int64_t>(pl, o_heap), heap);
         SC_LAUNCHED();
     }
     rg.tile_prefix = at<int32_t>(pl, o_pabs);
@@ -579,7 +603,32 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
     }
     if (pl->profile) if (int rc = prof_event(pl, 4 * group + 2, st)) return rc;
     rg.tile_prefix = at<int32_t>(pl, o_pb);
-    {
+    // vector form of pass B: every row start must be 16-byte aligned in all four buffers
+    bool vec_b = pl->use_b2 && pl->prm.n_mels % 8 == 0 && pl->prm.n_mfcc % 4 == 0 &&
+                 ((reinterpret_cast<uintptr_t>(pdb) | reinterpret_cast<uintptr_t>(mel) | reinterpret_cast<uintptr_t>(mfcc)) & 15) == 0;
+    for (int u = 0; u < n && vec_b; ++u) vec_b = (fo[u] & 3) == 0;
+    if (vec_b && pl->use_b3) {
+        B3Tile* btiles = reinterpret_cast<B3Tile*>(wb + w_b3);
+        rg.tile_prefix = at<int32_t>(pl, o_pb3);
+        k_b3_tiles<<<(pre_b3[n] + 255) / 256, 256, 0, st>>>(rg, pre_b3[n], btiles);
+        SC_LAUNCHED();
+        k_fe_c00<<<(n + 127) / 128, 128, 0, st>>>(rg, tb, fp, stat, mel_raw);
+        SC_LAUNCHED();
+        {
+            static int n_sm_b = 0;
+            if (!n_sm_b) SC_CUDA(cudaDeviceGetAttribute(&n_sm_b, cudaDevAttrMultiProcessorCount, pl->device));
+            const int grid = pre_b3[n] < 3 * n_sm_b ? pre_b3[n] : 3 * n_sm_b;
+            k_fe_pass_b3<<<grid, kB3Threads, 0, st>>>(btiles, pre_b3[n], tb, fp, stat, mel_raw, pdb, mel, mfcc);
+        }
+        SC_LAUNCHED();
+    } else if (vec_b) {
+        k_fe_c00<<<(n + 127) / 128, 128, 0, st>>>(rg, tb, fp, stat, mel_raw);
+        SC_LAUNCHED();
+        const size_t smem = fb2_layout(pl->prm.n_mels, pl->prm.n_mfcc).bytes;
+        SC_CUDA(cudaFuncSetAttribute(k_fe_pass_b2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_fe_pass_b2<<<pre_b[n], kFbThreads, smem, st>>>(rg, tb, fp, stat, mel_raw, pdb, mel, mfcc, pl->n_bins);
+        SC_LAUNCHED();
+    } else {
         const size_t smem = fb_layout(pl->prm.n_mels, pl->prm.n_mfcc).bytes;
         SC_CUDA(cudaFuncSetAttribute(k_fe_pass_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_fe_pass_b<<<pre_b[n], kFbThreads, smem, st>>>(rg, tb, fp, stat, mel_raw, pdb, mel, mfcc, pl->n_bins);
@@ -609,7 +658,8 @@ extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* s
     }
     // one allocation that fits every group (frontend_range never has to grow it mid-batch)
     const size_t bound = ((sizeof(UttStat) * n + 255) & ~size_t(255)) + ((sizeof(float) * (size_t)heap_total + 255) & ~size_t(255)) +
-                         256 + sizeof(float) * (size_t)max_row * pl->prm.n_mels;
+                         256 + sizeof(float) * (size_t)max_row * pl->prm.n_mels +
+                         1024 + ((size_t)max_row / 20 + 2 * (size_t)n + 16) * (sizeof(WsTile) + sizeof(B3Tile));   // tile records
     if (int rc = pl->work.ensure(bound)) return rc;
     // Groups of consecutive utterances whose raw dB intermediates (1 124 B/frame) stay L2-resident between
     // pass A and pass B: pass B then re-reads from L2 and the raw values are overwritten before they reach DRAM.
@@ -647,6 +697,7 @@ extern "C" int sc_mean_abs_batch(sc_plan* pl, const float* wav, const int64_t* s
     }
     Blob b;
     const size_t o_so = b.add(so), o_sl = b.add(slen), o_fo = b.add(fo), o_fc = b.add(fc), o_p = b.add(pre), o_h = b.add(heap_off);
+    const size_t o_arec = b.add(abs_recs(pre, n));
     if (int rc = upload_blob(pl, b, st)) return rc;
     const size_t w_heap = (sizeof(UttStat) * n + 255) & ~size_t(255);
     if (int rc = pl->work.ensure(w_heap + sizeof(float) * (size_t)heap_off[n])) return rc;
@@ -656,7 +707,8 @@ extern "C" int sc_mean_abs_batch(sc_plan* pl, const float* wav, const int64_t* s
     rg.frame_off = at<int64_t>(pl, o_fo); rg.frame_cnt = at<int32_t>(pl, o_fc);
     rg.tile_prefix = at<int32_t>(pl, o_p); rg.n_utts = n;
     float* heap = reinterpret_cast<float*>(wb + w_heap);
-    k_abs_pairwise<<<pre[n], kAbsThreads, 0, st>>>(wav, rg, at<int64_t>(pl, o_h), heap);
+    if (use_abs2()) k_abs_pairwise2<<<pre[n], kAbs2Threads, 0, st>>>(wav, rg, at<int2>(pl, o_arec), at<int64_t>(pl, o_h), heap);
+    else k_abs_pairwise<<<pre[n], kAbsThreads, 0, st>>>(wav, rg, at<int64_t>(pl, o_h), heap);
     SC_LAUNCHED();
     k_gain_finalize<<<(n + 3) / 4, 128, 0, st>>>(rg, at<int64_t>(pl, o_h), heap, reinterpret_cast<UttStat*>(wb), 1.0, 1, mean_out);
     SC_LAUNCHED();
