@@ -222,6 +222,200 @@ __global__ void __launch_bounds__(kAbs2Threads) k_abs_pairwise2(const float* __r
     }
 }
 
+// Third form of the leaf pass: the CTA stages its subtree (<= kAbsSubtree samples) in shared memory with coalesced
+// 128-bit loads, then ONE THREAD per depth-7 slot sums its leaf with NumPy's 8 accumulators held in registers
+// (two float4 per step: no shuffles, 1.25 instructions per sample).  The staged copy is padded by 4 words per 128
+// samples so that leaves that start 128 samples apart fall into different bank groups.
+constexpr int kAbs3Threads = 128;
+constexpr int kAbs3Smem = kAbsSubtree + 4 * (kAbsSubtree / 128 + 1);
+__device__ __forceinline__ int abs3_pos(int i) { return i + ((i >> 7) << 2); }
+__global__ void __launch_bounds__(kAbs3Threads) k_abs_pairwise3(const float* __restrict__ wav, Ragged rg,
+                                                                const int2* __restrict__ recs,
+                                                                const int64_t* __restrict__ heap_off,
+                                                                float* __restrict__ heap) {
+    __shared__ __align__(16) float buf[kAbs3Smem];
+    __shared__ __align__(16) float hv[128];
+    const int tid = threadIdx.x;
+    const int2 rec = __ldg(recs + blockIdx.x);
+    const int u = rec.x, idx = rec.y;
+    const int64_t len = rg.sample_len[u];
+    const int D = abs_depth(len);
+    int64_t start = 0, n64 = len;
+    for (int b = D - 1; b >= 0; --b) {
+        int64_t n2 = n64 / 2;
+        n2 -= n2 % 8;
+        if ((idx >> b) & 1) { start += n2; n64 -= n2; } else { n64 = n2; }
+    }
+    const float* __restrict__ a = wav + rg.sample_off[u] + start;
+    const int n = (int)n64;
+    // ---- stage: all loads first (<= 16 float4 per thread), then the padded stores
+    if ((reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+        constexpr int kIt = (kAbsSubtree / 4 + kAbs3Threads - 1) / kAbs3Threads;
+        const float4* __restrict__ a4 = reinterpret_cast<const float4*>(a);
+        const int n4 = n >> 2;
+        float4 v[kIt];
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+            const int e = tid + it * kAbs3Threads;
+            if (e < n4) v[it] = __ldg(a4 + e);
+        }
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+            const int e = tid + it * kAbs3Threads;
+            if (e < n4) *reinterpret_cast<float4*>(buf + abs3_pos(4 * e)) = v[it];
+        }
+        for (int e = (n4 << 2) + tid; e < n; e += kAbs3Threads) buf[abs3_pos(e)] = __ldg(a + e);
+    } else {
+        for (int e = tid; e < n; e += kAbs3Threads) buf[abs3_pos(e)] = __ldg(a + e);
+    }
+    // ---- bounds of this thread's depth-7 slot (see k_abs_pairwise2)
+    int o = 0, m = n;
+    bool first = true;
+#pragma unroll
+    for (int lvl = 6; lvl >= 0; --lvl) {
+        const int bit = (tid >> lvl) & 1;
+        if (m > 128) {
+            int n2 = m / 2;
+            n2 -= n2 % 8;
+            if (bit) { o += n2; m -= n2; } else { m = n2; }
+        } else if (bit) {
+            first = false;
+        }
+    }
+    __syncthreads();
+    float res = 0.f;
+    if (first && m > 0) {
+        // o is a multiple of 8 and a leaf never crosses more than one 128-sample pad boundary unaligned:
+        // pad boundaries are multiples of 128, float4 groups start at multiples of 4
+        if (m < 8) {
+            for (int k = 0; k < m; ++k) res += fabsf(buf[abs3_pos(o + k)]);
+        } else {
+            const int body = m - (m % 8);
+            float4 lo = *reinterpret_cast<const float4*>(buf + abs3_pos(o));
+            float4 hi = *reinterpret_cast<const float4*>(buf + abs3_pos(o + 4));
+            float r0 = fabsf(lo.x), r1 = fabsf(lo.y), r2 = fabsf(lo.z), r3 = fabsf(lo.w);
+            float r4 = fabsf(hi.x), r5 = fabsf(hi.y), r6 = fabsf(hi.z), r7 = fabsf(hi.w);
+#pragma unroll 4
+            for (int i = 8; i < body; i += 8) {
+                lo = *reinterpret_cast<const float4*>(buf + abs3_pos(o + i));
+                hi = *reinterpret_cast<const float4*>(buf + abs3_pos(o + i + 4));
+                r0 += fabsf(lo.x); r1 += fabsf(lo.y); r2 += fabsf(lo.z); r3 += fabsf(lo.w);
+                r4 += fabsf(hi.x); r5 += fabsf(hi.y); r6 += fabsf(hi.z); r7 += fabsf(hi.w);
+            }
+            res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+            for (int k = body; k < m; ++k) res += fabsf(buf[abs3_pos(o + k)]);
+        }
+    }
+    hv[tid] = res;
+    __syncthreads();
+    if (tid < 32) {
+        const float4 x = reinterpret_cast<const float4*>(hv)[tid];
+        float t = (x.x + x.y) + (x.z + x.w);
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) t += __shfl_xor_sync(0xffffffffu, t, s);
+        if (tid == 0) heap[heap_off[u] + (1 << D) + idx] = t;
+    }
+}
+
+// Fourth form: abs3's arithmetic in a persistent CTA.  Sub-tree records (source offset, length, heap slot) come
+// from k_fe_setup; the loads of sub-tree i+1 and the record of sub-tree i+2 are in flight while sub-tree i is
+// summed, so the kernel streams the audio instead of paying the record -> data latency chain once per CTA.
+struct AbsRec {
+    int64_t src_off;     // first sample of the sub-tree in the packed waveform buffer
+    int64_t heap_pos;    // where its sum goes
+    int32_t n, pad;
+};
+__global__ void __launch_bounds__(kAbs3Threads, 4) k_abs_pairwise4(const float* __restrict__ wav,
+                                                                   const AbsRec* __restrict__ recs, int total,
+                                                                   float* __restrict__ heap) {
+    __shared__ __align__(16) float buf[kAbs3Smem];
+    __shared__ __align__(16) float hv[128];
+    const int tid = threadIdx.x;
+    const int G = gridDim.x;
+    constexpr int kIt = (kAbsSubtree / 4 + kAbs3Threads - 1) / kAbs3Threads;
+    AbsRec dummy; dummy.src_off = 0; dummy.heap_pos = 0; dummy.n = 0; dummy.pad = 0;
+    int k = blockIdx.x;
+    AbsRec cur = k < total ? recs[k] : dummy;
+    AbsRec nxt = k + G < total ? recs[k + G] : dummy;
+    float4 v[kIt];
+    auto issue = [&](const AbsRec& r) {
+        const float* __restrict__ a = wav + r.src_off;
+        if ((reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+            const float4* __restrict__ a4 = reinterpret_cast<const float4*>(a);
+            const int n4 = r.n >> 2;
+#pragma unroll
+            for (int it = 0; it < kIt; ++it) {
+                const int e = tid + it * kAbs3Threads;
+                if (e < n4) v[it] = __ldg(a4 + e);
+            }
+        }
+    };
+    issue(cur);
+    for (; k < total; k += G) {
+        const float* __restrict__ a = wav + cur.src_off;
+        const int n = cur.n;
+        if ((reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+            const int n4 = n >> 2;
+#pragma unroll
+            for (int it = 0; it < kIt; ++it) {
+                const int e = tid + it * kAbs3Threads;
+                if (e < n4) *reinterpret_cast<float4*>(buf + abs3_pos(4 * e)) = v[it];
+            }
+            for (int e = (n4 << 2) + tid; e < n; e += kAbs3Threads) buf[abs3_pos(e)] = __ldg(a + e);
+        } else {
+            for (int e = tid; e < n; e += kAbs3Threads) buf[abs3_pos(e)] = __ldg(a + e);
+        }
+        const AbsRec nn = k + 2 * G < total ? recs[k + 2 * G] : dummy;
+        if (k + G < total) issue(nxt);
+        int o = 0, m = n;
+        bool first = true;
+#pragma unroll
+        for (int lvl = 6; lvl >= 0; --lvl) {
+            const int bit = (tid >> lvl) & 1;
+            if (m > 128) {
+                int n2 = m / 2;
+                n2 -= n2 % 8;
+                if (bit) { o += n2; m -= n2; } else { m = n2; }
+            } else if (bit) {
+                first = false;
+            }
+        }
+        __syncthreads();
+        float res = 0.f;
+        if (first && m > 0) {
+            if (m < 8) {
+                for (int q = 0; q < m; ++q) res += fabsf(buf[abs3_pos(o + q)]);
+            } else {
+                const int body = m - (m % 8);
+                float4 lo = *reinterpret_cast<const float4*>(buf + abs3_pos(o));
+                float4 hi = *reinterpret_cast<const float4*>(buf + abs3_pos(o + 4));
+                float r0 = fabsf(lo.x), r1 = fabsf(lo.y), r2 = fabsf(lo.z), r3 = fabsf(lo.w);
+                float r4 = fabsf(hi.x), r5 = fabsf(hi.y), r6 = fabsf(hi.z), r7 = fabsf(hi.w);
+#pragma unroll 4
+                for (int i = 8; i < body; i += 8) {
+                    lo = *reinterpret_cast<const float4*>(buf + abs3_pos(o + i));
+                    hi = *reinterpret_cast<const float4*>(buf + abs3_pos(o + i + 4));
+                    r0 += fabsf(lo.x); r1 += fabsf(lo.y); r2 += fabsf(lo.z); r3 += fabsf(lo.w);
+                    r4 += fabsf(hi.x); r5 += fabsf(hi.y); r6 += fabsf(hi.z); r7 += fabsf(hi.w);
+                }
+                res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+                for (int q = body; q < m; ++q) res += fabsf(buf[abs3_pos(o + q)]);
+            }
+        }
+        hv[tid] = res;
+        __syncthreads();
+        if (tid < 32) {
+            const float4 x = reinterpret_cast<const float4*>(hv)[tid];
+            float t = (x.x + x.y) + (x.z + x.w);
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) t += __shfl_xor_sync(0xffffffffu, t, s);
+            if (tid == 0) heap[cur.heap_pos] = t;
+        }
+        cur = nxt;
+        nxt = nn;
+    }
+}
+
 __global__ void __launch_bounds__(128) k_gain_finalize(Ragged rg, const int64_t* __restrict__ heap_off,
                                                        float* __restrict__ heap, UttStat* __restrict__ stat,
                                                        double mean_abs_amp_norm, int use_gain,
@@ -852,8 +1046,10 @@ k_fe_pass_b(Ragged rg, FeTables tb, FeParams prm, const UttStat* __restrict__ st
 // MFCC[0, 0] - MFCC[0, 0] is exactly 0 like the reference's.
 __global__ void __launch_bounds__(128) k_fe_c00(Ragged rg, FeTables tb, FeParams prm, UttStat* __restrict__ stat,
                                                 const float* __restrict__ mel_raw) {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per utterance: the loads run in parallel, the 40-term FMA chain is replayed in order through shuffles
+    const int u = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (u >= rg.n_utts) return;
+    const int lane = threadIdx.x & 31;
     float a = 0.f;
     if (prm.norm_first) {
         const int n_mels = tb.n_mels;
@@ -861,13 +1057,24 @@ __global__ void __launch_bounds__(128) k_fe_c00(Ragged rg, FeTables tb, FeParams
         const float m_floor = 2.0f * db10(fmaxf(__uint_as_float(stat[u].m_max), 1e-5f)) - 80.0f;
         const float* __restrict__ src = mel_raw + rg.frame_off[u] * n_mels;
         const int pairs = n_mels / 2;
-        for (int n = 0; n < L.half; ++n) {
-            const float x1 = fmaxf(__ldg(src + n), m_floor);
-            const float x2 = n < pairs ? fmaxf(__ldg(src + (n_mels - 1 - n)), m_floor) : 0.f;
-            a = fmaf(__ldg(tb.dct_e + n * L.ne_pad), n < pairs ? x1 + x2 : x1, a);
+        float sv[2], ev[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int n = lane + 32 * q;
+            sv[q] = 0.f; ev[q] = 0.f;
+            if (n < L.half) {
+                const float x1 = fmaxf(__ldg(src + n), m_floor);
+                const float x2 = n < pairs ? fmaxf(__ldg(src + (n_mels - 1 - n)), m_floor) : 0.f;
+                sv[q] = n < pairs ? x1 + x2 : x1;
+                ev[q] = __ldg(tb.dct_e + n * L.ne_pad);
+            }
         }
+        for (int n = 0; n < min(L.half, 32); ++n)
+            a = fmaf(__shfl_sync(0xffffffffu, ev[0], n), __shfl_sync(0xffffffffu, sv[0], n), a);
+        for (int n = 32; n < L.half; ++n)
+            a = fmaf(__shfl_sync(0xffffffffu, ev[1], n - 32), __shfl_sync(0xffffffffu, sv[1], n - 32), a);
     }
-    stat[u].pad[0] = a;
+    if (lane == 0) stat[u].pad[0] = a;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -73,6 +73,63 @@ __global__ void k_ws_tiles(Ragged rg, int total_tiles, WsTile* __restrict__ out)
     out[tile] = t;
 }
 
+// One launch that writes every per-call table of the fast front-end path: the sub-tree records of the |y| sum,
+// the tiles of k_fe_pass_a_ws and the tiles of k_fe_pass_b3, and resets the per-utterance statistics is left to
+// k_gain_finalize.  Thread id space: [0, n_abs) | [n_abs, n_abs + n_ws) | [.., + n_b3).
+struct SetupArgs {
+    const int32_t* pre_abs; const int32_t* pre_ws; const int32_t* pre_b3;
+    const int64_t* heap_off;
+    int32_t n_abs, n_ws, n_b3;
+    AbsRec* abs_out; WsTile* ws_out; B3Tile* b3_out;
+};
+__global__ void k_fe_setup(Ragged rg, SetupArgs sa) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < sa.n_abs) {
+        const int u = find_utt(sa.pre_abs, rg.n_utts, i);
+        const int idx = i - sa.pre_abs[u];
+        const int64_t len = rg.sample_len[u];
+        const int D = abs_depth(len);
+        int64_t start = 0, n = len;
+        for (int b = D - 1; b >= 0; --b) {
+            int64_t n2 = n / 2;
+            n2 -= n2 % 8;
+            if ((idx >> b) & 1) { start += n2; n -= n2; } else { n = n2; }
+        }
+        AbsRec r;
+        r.src_off = rg.sample_off[u] + start;
+        r.heap_pos = sa.heap_off[u] + (int64_t(1) << D) + idx;
+        r.n = (int)n; r.pad = 0;
+        sa.abs_out[i] = r;
+        return;
+    }
+    i -= sa.n_abs;
+    if (i < sa.n_ws) {
+        const int u = find_utt(sa.pre_ws, rg.n_utts, i);
+        WsTile t;
+        t.u = u;
+        t.t0 = (i - sa.pre_ws[u]) * kWsFrames;
+        t.nfr = min(kWsFrames, rg.frame_cnt[u] - t.t0);
+        t.L = rg.sample_len[u];
+        t.sample_off = rg.sample_off[u];
+        t.frame_row = rg.frame_off[u] + t.t0;
+        const int64_t q0 = (int64_t)t.t0 * kHop - kNfft / 2;
+        t.edge = !(q0 - 4 >= 0 && q0 + kWsSpan + 4 <= t.L);
+        sa.ws_out[i] = t;
+        return;
+    }
+    i -= sa.n_ws;
+    if (i < sa.n_b3) {
+        const int u = find_utt(sa.pre_b3, rg.n_utts, i);
+        B3Tile t;
+        t.u = u;
+        t.t0 = (i - sa.pre_b3[u]) * kB3Frames;
+        t.T = rg.frame_cnt[u];
+        t.frame_off = rg.frame_off[u];
+        t.pad = 0;
+        sa.b3_out[i] = t;
+    }
+}
+
 // ---- mbarrier / bulk-copy primitives (PTX)
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, unsigned count) {

@@ -446,10 +446,12 @@ static std::vector<int2> abs_recs(const std::vector<int32_t>& pre, int n) {
         for (int i = pre[u]; i < pre[u + 1]; ++i) r[i] = make_int2(u, i - pre[u]);
     return r;
 }
-static bool use_abs2() {
+// leaf pass of the |y| sum: 4 = persistent staged (default on the fast path), 3 = staged, thread per leaf;
+// 2 = 8 lanes per slot; 1 = shared-memory heap
+static int abs_variant() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("SC_FE_ABS2"); v = e ? atoi(e) != 0 : 1; }
-    return v != 0;
+    if (v < 0) { const char* e = getenv("SC_FE_ABS"); v = e ? atoi(e) : 4; }
+    return v;
 }
 // one L2-resident group of utterances [0, n) (pointers already offset by the caller)
 static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, const int64_t* slen_in, int32_t n,
@@ -507,7 +509,8 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
     const size_t w_mel = (w_part + sizeof(float) * (size_t)heap_off[n] + 255) & ~size_t(255);
     const size_t w_tiles = (w_mel + sizeof(float) * (size_t)total_frames_span * pl->prm.n_mels + 255) & ~size_t(255);
     const size_t w_b3 = (w_tiles + (ws ? sizeof(WsTile) * (size_t)pre_int[n] : 0) + 255) & ~size_t(255);
-    const size_t w_end = w_b3 + sizeof(B3Tile) * (size_t)pre_b3[n];
+    const size_t w_arec = (w_b3 + sizeof(B3Tile) * (size_t)pre_b3[n] + 255) & ~size_t(255);
+    const size_t w_end = w_arec + sizeof(AbsRec) * (size_t)pre_abs[n];
     if (int rc = pl->work.ensure(w_end)) return rc;
     unsigned char* wb = static_cast<unsigned char*>(pl->work.p);
     UttStat* stat = reinterpret_cast<UttStat*>(wb + w_stat);
@@ -523,9 +526,34 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
     const FeParams fp = fe_params(pl);
 
     if (pl->profile) { if (int rc = prof_event(pl, 4 * group, st)) return rc; pl->pev_kind = 1; pl->pev_groups = group + 1; }
+    // one launch writes every per-call table of the fast path (sub-tree records, pass A tiles, pass B tiles)
+    const bool b3 = pl->fast && pl->use_b3 && pl->use_b2;
+    const bool setup = pl->fast && (ws || b3 || abs_variant() == 4);
+    static int n_sm_all = 0;
+    if (!n_sm_all) SC_CUDA(cudaDeviceGetAttribute(&n_sm_all, cudaDevAttrMultiProcessorCount, pl->device));
+    if (setup) {
+        SetupArgs sa;
+        sa.pre_abs = at<int32_t>(pl, o_pabs); sa.pre_ws = at<int32_t>(pl, o_pint); sa.pre_b3 = at<int32_t>(pl, o_pb3);
+        sa.heap_off = at<int64_t>(pl, o_heap);
+        sa.n_abs = (fp.use_gain && abs_variant() == 4) ? pre_abs[n] : 0;
+        sa.n_ws = ws ? pre_int[n] : 0;
+        sa.n_b3 = b3 ? pre_b3[n] : 0;
+        sa.abs_out = reinterpret_cast<AbsRec*>(wb + w_arec);
+        sa.ws_out = reinterpret_cast<WsTile*>(wb + w_tiles);
+        sa.b3_out = reinterpret_cast<B3Tile*>(wb + w_b3);
+        const int total = sa.n_abs + sa.n_ws + sa.n_b3;
+        if (total > 0) {
+            k_fe_setup<<<(total + 255) / 256, 256, 0, st>>>(rg, sa);
+            SC_LAUNCHED();
+        }
+    }
     if (fp.use_gain) {
         rg.tile_prefix = at<int32_t>(pl, o_pabs);
-        if (use_abs2()) k_abs_pairwise2<<<pre_abs[n], kAbs2Threads, 0, st>>>(wav, rg, at<int2>(pl, o_arec), at<int64_t>(pl, o_heap), heap);
+        if (pl->fast && abs_variant() == 4) {
+            const int grid = pre_abs[n] < 4 * n_sm_all ? pre_abs[n] : 4 * n_sm_all;
+            k_abs_pairwise4<<<grid, kAbs3Threads, 0, st>>>(wav, reinterpret_cast<const AbsRec*>(wb + w_arec), pre_abs[n], heap);
+        } else if (abs_variant() >= 3) k_abs_pairwise3<<<pre_abs[n], kAbs3Threads, 0, st>>>(wav, rg, at<int2>(pl, o_arec), at<int64_t>(pl, o_heap), heap);
+        else if (abs_variant() == 2) k_abs_pairwise2<<<pre_abs[n], kAbs2Threads, 0, st>>>(wav, rg, at<int2>(pl, o_arec), at<int64_t>(pl, o_heap), heap);
         else k_abs_pairwise<<<pre_abs[n], kAbsThreads, 0, st>>>(wav, rg, at<int64_t>(pl, o_heap), heap);
         SC_LAUNCHED();
     }
@@ -560,9 +588,6 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
                 ws_attr = true;
             }
             WsTile* tiles = reinterpret_cast<WsTile*>(wb + w_tiles);
-            rg.tile_prefix = at<int32_t>(pl, o_pint);
-            k_ws_tiles<<<(pre_int[n] + 255) / 256, 256, 0, st>>>(rg, pre_int[n], tiles);
-            SC_LAUNCHED();
             const int grid = pre_int[n] < n_sm ? pre_int[n] : n_sm;
             if (pl->fp32_fft)
                 k_fe_pass_a_ws<float><<<grid, kWsThreads, sizeof(WsSmem<float>) + mel_s_bytes, st>>>(
@@ -607,12 +632,9 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
     bool vec_b = pl->use_b2 && pl->prm.n_mels % 8 == 0 && pl->prm.n_mfcc % 4 == 0 &&
                  ((reinterpret_cast<uintptr_t>(pdb) | reinterpret_cast<uintptr_t>(mel) | reinterpret_cast<uintptr_t>(mfcc)) & 15) == 0;
     for (int u = 0; u < n && vec_b; ++u) vec_b = (fo[u] & 3) == 0;
-    if (vec_b && pl->use_b3) {
+    if (vec_b && b3) {
         B3Tile* btiles = reinterpret_cast<B3Tile*>(wb + w_b3);
-        rg.tile_prefix = at<int32_t>(pl, o_pb3);
-        k_b3_tiles<<<(pre_b3[n] + 255) / 256, 256, 0, st>>>(rg, pre_b3[n], btiles);
-        SC_LAUNCHED();
-        k_fe_c00<<<(n + 127) / 128, 128, 0, st>>>(rg, tb, fp, stat, mel_raw);
+        k_fe_c00<<<(n + 3) / 4, 128, 0, st>>>(rg, tb, fp, stat, mel_raw);
         SC_LAUNCHED();
         {
             static int n_sm_b = 0;
@@ -622,7 +644,7 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
         }
         SC_LAUNCHED();
     } else if (vec_b) {
-        k_fe_c00<<<(n + 127) / 128, 128, 0, st>>>(rg, tb, fp, stat, mel_raw);
+        k_fe_c00<<<(n + 3) / 4, 128, 0, st>>>(rg, tb, fp, stat, mel_raw);
         SC_LAUNCHED();
         const size_t smem = fb2_layout(pl->prm.n_mels, pl->prm.n_mfcc).bytes;
         SC_CUDA(cudaFuncSetAttribute(k_fe_pass_b2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -659,7 +681,8 @@ extern "C" int sc_frontend_batch(sc_plan* pl, const float* wav, const int64_t* s
     // one allocation that fits every group (frontend_range never has to grow it mid-batch)
     const size_t bound = ((sizeof(UttStat) * n + 255) & ~size_t(255)) + ((sizeof(float) * (size_t)heap_total + 255) & ~size_t(255)) +
                          256 + sizeof(float) * (size_t)max_row * pl->prm.n_mels +
-                         1024 + ((size_t)max_row / 20 + 2 * (size_t)n + 16) * (sizeof(WsTile) + sizeof(B3Tile));   // tile records
+                         1024 + ((size_t)max_row / 20 + 2 * (size_t)n + 16) * (sizeof(WsTile) + sizeof(B3Tile)) +
+                         256 + sizeof(AbsRec) * (size_t)(heap_total / 2);   // tile and sub-tree records
     if (int rc = pl->work.ensure(bound)) return rc;
     // Groups of consecutive utterances whose raw dB intermediates (1 124 B/frame) stay L2-resident between
     // pass A and pass B: pass B then re-reads from L2 and the raw values are overwritten before they reach DRAM.
@@ -707,7 +730,8 @@ extern "C" int sc_mean_abs_batch(sc_plan* pl, const float* wav, const int64_t* s
     rg.frame_off = at<int64_t>(pl, o_fo); rg.frame_cnt = at<int32_t>(pl, o_fc);
     rg.tile_prefix = at<int32_t>(pl, o_p); rg.n_utts = n;
     float* heap = reinterpret_cast<float*>(wb + w_heap);
-    if (use_abs2()) k_abs_pairwise2<<<pre[n], kAbs2Threads, 0, st>>>(wav, rg, at<int2>(pl, o_arec), at<int64_t>(pl, o_h), heap);
+    if (abs_variant() >= 3) k_abs_pairwise3<<<pre[n], kAbs3Threads, 0, st>>>(wav, rg, at<int2>(pl, o_arec), at<int64_t>(pl, o_h), heap);
+    else if (abs_variant() == 2) k_abs_pairwise2<<<pre[n], kAbs2Threads, 0, st>>>(wav, rg, at<int2>(pl, o_arec), at<int64_t>(pl, o_h), heap);
     else k_abs_pairwise<<<pre[n], kAbsThreads, 0, st>>>(wav, rg, at<int64_t>(pl, o_h), heap);
     SC_LAUNCHED();
     k_gain_finalize<<<(n + 3) / 4, 128, 0, st>>>(rg, at<int64_t>(pl, o_h), heap, reinterpret_cast<UttStat*>(wb), 1.0, 1, mean_out);
