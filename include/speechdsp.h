@@ -89,6 +89,20 @@ int sc_frontend_batch(sc_plan* plan, const float* wav_dev, const int64_t* sample
 int sc_mean_abs_batch(sc_plan* plan, const float* wav_dev, const int64_t* sample_offsets_host,
                       const int64_t* sample_lengths_host, int32_t n_utts, float* mean_out_dev, void* stream);
 
+/* calc_PHN_target (audio_lib.py:51-85; callers TIMIT_reader.py:192, ARCTIC_reader.py:157,
+ * TARGET_spk_reader.py:173) over a ragged batch: for every frame, the index (within its utterance's
+ * interval list) of the phoneme interval that the reference's cursor + larger-overlap rule selects.
+ *   phn_start_dev / phn_end_dev   packed int32 interval bounds in samples, [start, end)
+ *   phn_offsets_host              n_utts+1: utterance u owns intervals [phn_offsets[u], phn_offsets[u+1]),
+ *                                 at least one, ends in non-decreasing order (checked by the caller)
+ *   sample_lengths_host           samples per utterance: frames = 1 + len / hop_length (:52)
+ *   out_index_dev                 int32 per frame at row frame_offsets_host[u] + t
+ * The caller maps indices to labels (phn_conv_d[phn_v[i][2]], :72-79). */
+int sc_phn_target_batch(sc_plan* plan, const int32_t* phn_start_dev, const int32_t* phn_end_dev,
+                        const int64_t* phn_offsets_host, const int64_t* sample_lengths_host, int32_t n_utts,
+                        int32_t hop_length, int32_t win_length, int32_t* out_index_dev,
+                        const int64_t* frame_offsets_host, void* stream);
+
 /* calc_preemphasis / calc_inv_preemphasis (audio_lib.py:12-28, :31-47): float32 in, float64 out
  * (scipy.signal.lfilter promotes), zero initial state, one signal of n samples. */
 int sc_preemphasis(const float* wav_dev, int64_t n, double coeff, double* out_dev, void* stream);

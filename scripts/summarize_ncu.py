@@ -3,6 +3,7 @@
 
     python scripts/summarize_ncu.py launches <launches.csv> <out.md>      # --metrics gpu__time_duration.sum list
     python scripts/summarize_ncu.py full <prof.ncu-rep> <out.md>          # --set full capture (needs ncu here)
+    python scripts/summarize_ncu.py traffic <prof.ncu-rep> <out.json>     # DRAM bytes per launch for bench.py's roofline.traffic
 """
 import collections
 import csv
@@ -84,5 +85,33 @@ def full(src, dst):
             f.write(f"| {label} | " + " | ".join(cells) + " |\n")
 
 
+GROUPS = [   # bench.py roofline groups -> kernels of one front-end step
+    ("gain: k_fe_setup + k_abs_pairwise4 + k_gain_finalize", ("k_fe_setup", "k_abs_pairwise", "k_gain_finalize")),
+    ("pass A: k_fe_pass_a_ws", ("k_fe_pass_a",)),
+    ("pass B: k_fe_c00 + k_fe_pass_b3", ("k_fe_c00", "k_fe_pass_b", "k_b3_tiles")),
+    ("k_gl_iter_persist", ("k_gl_iter_persist",)),
+]
+
+
+def traffic(src, dst):
+    """DRAM read + write bytes per launch (last = warm launch of every kernel), summed per bench group."""
+    import json
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    seen = collections.OrderedDict()
+    for r in rows[2:]:
+        seen[r[ki].split("(")[0].split("::")[-1]] = float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]]
+    res = {"_source": f"{src}: dram__bytes_read.sum + dram__bytes_write.sum per launch (last launch of each kernel), "
+                      "ncu --set full, config-2 front-end shape (256 x 4 s) and config-3 Griffin-Lim shape",
+           "_kernels": seen}
+    for name, pats in GROUPS:
+        res[name] = sum(v for k, v in seen.items() if any(k.startswith(p_) or ("<" in k and k.split("<")[0].endswith(p_)) or p_ in k for p_ in pats))
+    with open(dst, "w") as f:
+        json.dump(res, f, indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])

@@ -48,6 +48,7 @@ PROTOTYPES = {
     "sc_num_frames": (C.c_int64, [_P, C.c_int64]),
     "sc_frontend_batch": (C.c_int, [_P, _P, _I64P, _I64P, C.c_int32, _P, _P, _P, _I64P, _P]),
     "sc_mean_abs_batch": (C.c_int, [_P, _P, _I64P, _I64P, C.c_int32, _P, _P]),
+    "sc_phn_target_batch": (C.c_int, [_P, _P, _P, _I64P, _I64P, C.c_int32, C.c_int32, C.c_int32, _P, _I64P, _P]),
     "sc_preemphasis": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P]),
     "sc_inv_preemphasis": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P]),
     "sc_power_to_amp_batch": (C.c_int, [_P, _P, _I64P, _I64P, C.c_int32, C.c_double, C.c_double, _P, _P]),

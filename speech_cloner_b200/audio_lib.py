@@ -334,31 +334,84 @@ def calc_inv_preemphasis(preem_wav, coeff=0.97):
     return _emphasis(preem_wav, coeff, inverse=True)
 
 
-def calc_PHN_target(y, phn_v, phn_conv_d, hop_length=40, win_length=400):
-    """Per-frame phoneme label by larger window overlap (audio_lib.py:51-85); host integer logic.
-
-    Out of the GPU hot path (SURVEY.md §2.1 #5, §8(f) "next"); kept so that the readers' loop
-    (TIMIT_reader.py:192) finds the whole ``audio_lib`` surface here.
-    """
-    n_frames = int(y.shape[0] / hop_length) + 1
-    starts = np.asarray([p[0] for p in phn_v], dtype=np.int64)
-    ends = np.asarray([p[1] for p in phn_v], dtype=np.int64)
-    last = len(phn_v) - 1
+def _phn_pick_host(n_samples: int, starts, ends, hop_length: int, win_length: int) -> np.ndarray:
+    """Index of the interval calc_PHN_target selects for every frame (audio_lib.py:56-79), on the host."""
+    n_frames = int(n_samples / hop_length) + 1
+    last = len(starts) - 1
     lo = np.arange(n_frames, dtype=np.int64) * hop_length - win_length // 2
     hi = lo + win_length
-    # the reference cursor only moves forward while ends[cur] <= lo: that is a running maximum of
-    # "first interval whose end exceeds lo" over frames (lo is increasing)
-    cur = np.empty(n_frames, dtype=np.int64)
-    c = 0
-    for t in range(n_frames):
-        while ends[c] <= lo[t] and c < last:
-            c += 1
-        cur[t] = c
+    if np.all(np.diff(ends) >= 0):
+        # sorted ends: the reference's forward-only cursor is "first interval whose end exceeds lo"
+        cur = np.minimum(np.searchsorted(ends, lo, side="right"), last)
+    else:
+        cur = np.empty(n_frames, dtype=np.int64)
+        c = 0
+        for t in range(n_frames):
+            while ends[c] <= lo[t] and c < last:
+                c += 1
+            cur[t] = c
     nxt = np.minimum(cur + 1, last)
     ov_cur = np.minimum(ends[cur], hi) - np.maximum(starts[cur], lo)
     ov_nxt = np.minimum(ends[nxt], hi) - np.maximum(starts[nxt], lo)
-    pick = np.where((cur < last) & (ov_cur < ov_nxt), nxt, cur)
+    return np.where((cur < last) & (ov_cur < ov_nxt), nxt, cur)
+
+
+def calc_PHN_target(y, phn_v, phn_conv_d, hop_length=40, win_length=400):
+    """Per-frame phoneme label by larger window overlap (audio_lib.py:51-85).
+
+    One utterance: integer logic on the host, exactly the reference's cursor.  The dataset-cache builders
+    (TIMIT_reader.py:192 and friends) use :func:`calc_PHN_target_batch`, which runs it on the device.
+    """
+    starts = np.asarray([p[0] for p in phn_v], dtype=np.int64)
+    ends = np.asarray([p[1] for p in phn_v], dtype=np.int64)
+    pick = _phn_pick_host(int(y.shape[0]), starts, ends, hop_length, win_length)
     return np.array([phn_conv_d[phn_v[i][2]] for i in pick], dtype=np.int32)
+
+
+def calc_PHN_target_batch(lengths, phn_vs, phn_conv_d, hop_length=40, win_length=400, return_index=False):
+    """``calc_PHN_target`` for a batch of utterances in one launch (``sc_phn_target_batch``).
+
+    ``lengths[u]`` is ``y.shape[0]`` of utterance u (or the waveform itself), ``phn_vs[u]`` its list of
+    ``(start, end, label)``.  Returns a list of int32 label arrays like the reference's (``phn_conv_d`` applied
+    on the host: it may map to one-hot vectors), or the selected interval indices when ``return_index``.
+    Interval ends must be non-decreasing inside an utterance (true for .PHN files); otherwise ValueError.
+    """
+    torch = _require_cuda()
+    lens = [int(n.shape[0]) if hasattr(n, "shape") else int(n) for n in lengths]
+    if len(lens) != len(phn_vs):
+        raise ValueError("lengths and phn_vs differ in length")
+    starts, ends, off = [], [], [0]
+    for v in phn_vs:
+        if len(v) == 0:
+            raise ValueError("every utterance needs at least one phoneme interval")
+        e = [int(p[1]) for p in v]
+        if any(b < a for a, b in zip(e, e[1:])):
+            raise ValueError("phoneme interval ends must be non-decreasing (use calc_PHN_target for unsorted lists)")
+        starts.extend(int(p[0]) for p in v)
+        ends.extend(e)
+        off.append(off[-1] + len(v))
+    frames = [int(n / hop_length) + 1 for n in lens]
+    fo = [0]
+    for t in frames:
+        fo.append(fo[-1] + t)
+    plan = DspPlan.get(n_fft=400, win_length=400, hop_length=80)        # any plan: only its descriptor staging is used
+    s_dev = torch.tensor(starts, dtype=torch.int32, device="cuda")
+    e_dev = torch.tensor(ends, dtype=torch.int32, device="cuda")
+    out = torch.empty(fo[-1], dtype=torch.int32, device="cuda")
+    rc = plan._lib.sc_phn_target_batch(plan._h, s_dev.data_ptr(), e_dev.data_ptr(), _lib.i64_array(off),
+                                       _lib.i64_array(lens), len(lens), int(hop_length), int(win_length),
+                                       out.data_ptr(), _lib.i64_array(fo), _stream_ptr(torch))
+    _lib.check(rc, "sc_phn_target_batch")
+    idx = out.cpu().numpy()
+    res = []
+    for u, v in enumerate(phn_vs):
+        pick = idx[fo[u]:fo[u + 1]]
+        if return_index:
+            res.append(pick.copy())
+        else:
+            table = np.array([phn_conv_d[p[2]] for p in v], dtype=np.int32)
+            res.append(table[pick])
+    return res
 
 
 # --------------------------------------------------------------------------- Griffin-Lim

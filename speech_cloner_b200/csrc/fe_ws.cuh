@@ -155,15 +155,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* b, unsigned parity) {
         : "memory");
     return ok != 0;
 }
-// Waiting warps sleep between probes so that they do not take issue slots from the warps they wait for.
-// A lost arrival would hang the GPU: trap instead after ~1 s so the host sees an error.
+// the same probe, but the hardware may park the warp for up to `ns` nanoseconds waiting for the phase to complete
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* b, unsigned parity, unsigned ns) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(b)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
+// Waiting warps are parked by the hardware (suspend-time hint) so that they do not take issue slots from the
+// warps they wait for.  A lost arrival would hang the GPU: trap instead after ~1 s so the host sees an error.
 __device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
     if (mbar_try_wait(b, parity)) return;
     unsigned spins = 0;
-    while (true) {
-        __nanosleep(40);
-        if (mbar_try_wait(b, parity)) return;
-        if (++spins > (1u << 24)) __trap();
+    while (!mbar_try_wait_hint(b, parity, 4000)) {
+        if (++spins > (1u << 20)) __trap();
     }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {

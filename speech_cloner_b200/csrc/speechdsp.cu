@@ -14,6 +14,7 @@
 #include "fe_ws.cuh"
 #include "gl_kernels.cuh"
 #include "generic_kernels.cuh"
+#include "phn_kernels.cuh"
 
 using namespace scdsp;
 
@@ -736,6 +737,41 @@ extern "C" int sc_mean_abs_batch(sc_plan* pl, const float* wav, const int64_t* s
     SC_LAUNCHED();
     k_gain_finalize<<<(n + 3) / 4, 128, 0, st>>>(rg, at<int64_t>(pl, o_h), heap, reinterpret_cast<UttStat*>(wb), 1.0, 1, mean_out);
     SC_LAUNCHED();
+    return SC_OK;
+}
+
+// --------------------------------------------------------------------------- frame labels
+extern "C" int sc_phn_target_batch(sc_plan* pl, const int32_t* phn_start, const int32_t* phn_end, const int64_t* phn_off,
+                                   const int64_t* slen, int32_t n, int32_t hop, int32_t win, int32_t* out_index,
+                                   const int64_t* foff, void* stream) {
+    if (!pl || !phn_start || !phn_end || !phn_off || !slen || !out_index || !foff)
+        return fail(SC_ERR_INVALID, "sc_phn_target_batch: null argument");
+    if (n <= 0) return SC_OK;
+    if (hop < 1 || win < 1) return fail(SC_ERR_INVALID, "sc_phn_target_batch: hop_length and win_length must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<int64_t> po(phn_off, phn_off + n + 1), fo(foff, foff + n);
+    std::vector<int32_t> fc(n);
+    int64_t max_t = 0;
+    for (int u = 0; u < n; ++u) {
+        if (po[u + 1] - po[u] < 1) return fail(SC_ERR_INVALID, "sc_phn_target_batch: every utterance needs at least one interval");
+        if (slen[u] < 0) return fail(SC_ERR_INVALID, "sc_phn_target_batch: negative length");
+        const int64_t T = 1 + slen[u] / hop;
+        if (T > INT32_MAX) return fail(SC_ERR_INVALID, "sc_phn_target_batch: utterance too long");
+        fc[u] = (int32_t)T;
+        if (T > max_t) max_t = T;
+    }
+    Blob b;
+    const size_t o_po = b.add(po), o_fo = b.add(fo), o_fc = b.add(fc);
+    if (int rc = upload_blob(pl, b, st)) return rc;
+    PhnBatch pb;
+    pb.start = phn_start; pb.end = phn_end;
+    pb.phn_off = at<int64_t>(pl, o_po); pb.frame_off = at<int64_t>(pl, o_fo); pb.frame_cnt = at<int32_t>(pl, o_fc);
+    pb.n_utts = n; pb.hop = hop; pb.win = win;
+    for (int u0 = 0; u0 < n; u0 += 32768) {
+        const int ny = n - u0 < 32768 ? n - u0 : 32768;
+        k_phn_target<<<dim3((unsigned)((max_t + 255) / 256), (unsigned)ny), 256, 0, st>>>(pb, u0, out_index);
+        SC_LAUNCHED();
+    }
     return SC_OK;
 }
 
