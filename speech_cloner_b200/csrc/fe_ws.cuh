@@ -506,7 +506,7 @@ k_fe_pass_a_ws(const float* __restrict__ wav, const WsTile* __restrict__ tiles, 
         const int mb = mp.chunk[ew], me = mp.chunk[ew + 1];
         const int pr0 = mp.pair0[ew], pr1 = mp.pair0[ew + 1];
         const float kInf = __int_as_float(0x7f800000);
-        long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+        long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0;
         const long long t_begin = clock64();
         for (int i = 0; blockIdx.x + i * G < total_tiles; ++i) {
             const int b = i & 1, k = i >> 1;
@@ -592,6 +592,9 @@ k_fe_pass_a_ws(const float* __restrict__ wav, const WsTile* __restrict__ tiles, 
 #endif
             mbar_arrive(&sm.bar_pw_empty[b]);                  // the power tile is free again
             WS_TIMED(w3, asm volatile("bar.sync 3, %0;" ::"n"(kWsEpiThreads) : "memory"));
+#ifdef SC_WS_DEBUG
+            const long long t_c = clock64();
+#endif
             // ---- raw amplitude_to_db (:172) of the mel power, coalesced rows (at most 4 rows per warp: all loads first)
             {
                 constexpr int kRows = (kWsFrames + kWsEpiWarps - 1) / kWsEpiWarps;
@@ -619,6 +622,9 @@ k_fe_pass_a_ws(const float* __restrict__ wav, const WsTile* __restrict__ tiles, 
                     }
                 }
             }
+#ifdef SC_WS_DEBUG
+            w4 += clock64() - t_c;
+#endif
             // ---- utterance max / min: values are >= +0, so their bit patterns order like unsigned integers
             {
                 const unsigned u_pmax = __reduce_max_sync(0xffffffffu, __float_as_uint(p_max));
@@ -636,9 +642,9 @@ k_fe_pass_a_ws(const float* __restrict__ wav, const WsTile* __restrict__ tiles, 
         }
 #ifdef SC_WS_DEBUG
         if (blockIdx.x == 0 && lane == 0)
-            printf("epi warp %d: total %lld pw_full %lld pdb %lld mel %lld bar %lld\n", ew, clock64() - t_begin, w0, w1, w2, w3);
+            printf("epi warp %d: total %lld pw_full %lld pdb %lld mel %lld bar %lld copy %lld\n", ew, clock64() - t_begin, w0, w1, w2, w3, w4);
 #endif
-        (void)w0; (void)w1; (void)w2; (void)w3; (void)t_begin;
+        (void)w0; (void)w1; (void)w2; (void)w3; (void)w4; (void)t_begin;
     }
 }
 

@@ -311,7 +311,10 @@ extern "C" int sc_plan_create(const sc_params* p, sc_plan** out) {
         };
         std::vector<double> cost(nm);
         double total = 0;
-        for (int bnd = 0; bnd < nm; ++bnd) { cost[bnd] = 9.0 * blocks_of(bnd) + 8.0; total += cost[bnd]; }
+        // measured per band pair: ~350 cycles + ~105 per float4 block (role timing of the SC_WS_DEBUG build)
+        double ws_cost_block = 1.0, ws_cost_band = 3.4;
+        if (const char* e = getenv("SC_WS_COST_BAND")) ws_cost_band = atof(e);
+        for (int bnd = 0; bnd < nm; ++bnd) { cost[bnd] = ws_cost_block * blocks_of(bnd) + ws_cost_band; total += cost[bnd]; }
         WsMelParam& wm = pl->ws_mel;
         wm.n_mels = nm;
         wm.chunk[0] = 0;
