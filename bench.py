@@ -34,7 +34,15 @@ import time
 # the CPU legs count cores explicitly: one BLAS/OpenMP thread per process (set before numpy loads)
 for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
     os.environ.setdefault(_k, "1")
-os.environ["NCCL_DEBUG"] = "WARN"     # stdout carries exactly one JSON line (no NCCL version banner)
+# stdout carries exactly one JSON line: everything else that libraries write to file descriptor 1 (NCCL's version
+# banner, ...) is sent to stderr, and the line itself goes to the saved descriptor (emit()).
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
 
 import numpy as np  # noqa: E402
 
@@ -152,7 +160,7 @@ def run_reference(args):
         dt = (time.perf_counter() - t) / args.steps
     val = audio_s / dt
     sample = f"{sample_n} of the 256 utterances x {SECONDS:g} s per step, multiprocessing.Pool({cores})"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "audio-seconds/second, front-end (calc_MFCC_input)", "value": val,
         "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -160,7 +168,7 @@ def run_reference(args):
         "config": {"workload": "frontend configs[1]: 256 x 4 s ARCTIC-shaped, hp/ds_dec_cfg_d.json", "sample": sample},
         "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------ GPU legs
@@ -477,7 +485,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "frontend_fp32_mode": alt, "griffin_lim": gl, "sweep_10h": sweep,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

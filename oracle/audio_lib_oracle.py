@@ -396,3 +396,35 @@ def from_power_to_wav(P,
     if pre_emphasis != 0:                                                  # :301-304
         y = calc_inv_preemphasis(y, pre_emphasis)
     return y * (mean_abs_amp_norm / np.abs(y).mean())                      # :306
+
+
+def compound(y0, y1):
+    """test.py:46-84 — stitch window predictions: ``y0`` (N, T, X) on the window grid, ``y1`` (N-1, T, X) on the
+    half-offset grid; the middle halves alternate between the two, the first / last window keep their outer 3/4.
+    Literal transcription (test infrastructure for speech_cloner_b200.conversion)."""
+    n_quarter = y0.shape[1] // 4
+    i_0, i_1 = 1, 0
+    y_v = [y0[0, :-n_quarter, :]]
+    while True:
+        do_break = True
+        if i_1 < y1.shape[0]:
+            y_v.append(y1[i_1, n_quarter:-n_quarter, :])
+            i_1 += 1
+            do_break = False
+        if i_0 < y0.shape[0] - 1:
+            y_v.append(y0[i_0, n_quarter:-n_quarter, :])
+            i_0 += 1
+            do_break = False
+        if do_break:
+            break
+    y_v.append(y0[-1, n_quarter:, :])
+    return np.concatenate(y_v, axis=0)
+
+
+def normalize_wav(y):
+    """librosa.output.write_wav(..., norm=True) (test.py:177-179) = librosa.util.normalize(y, norm=inf):
+    divide by max|y| unless it is below the dtype's tiny."""
+    y = np.asarray(y)
+    mag = np.max(np.abs(y)) if y.size else 0.0
+    tiny = np.finfo(y.dtype if np.issubdtype(y.dtype, np.floating) else np.float32).tiny
+    return y if mag < tiny else y / mag

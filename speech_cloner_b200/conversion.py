@@ -1,0 +1,74 @@
+"""Conversion glue either side of Griffin-Lim: ``compound`` stitching of the decoder's
+window predictions (test.py:46-84) and the peak normalisation of ``write_wav(norm=True)`` (test.py:177-179).
+
+Both keep the data where it is: CUDA tensors in -> CUDA tensors out, so a decoder's device output can be stitched,
+inverted by ``from_power_to_wav`` and normalised without a host round trip; NumPy in -> NumPy out reproduces the
+reference's slicing.  No arithmetic happens here except one division by the peak.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+
+from . import audio_lib as al
+
+
+def compound_segments(n0: int, n1: int, T: int) -> List[Tuple[int, int, int, int]]:
+    """The slices ``compound`` concatenates, as (source 0|1, window index, start, stop): the reference loop
+    (test.py:54-79) unrolled.  First window of y0 keeps [0, T - T//4), then the middle halves of y1[0], y0[1],
+    y1[1], ... while either has windows left, and the last window of y0 contributes [T//4, T)."""
+    q = T // 4
+    mid_stop = T - q if q else 0                       # x[q:-q] and x[:-q] are EMPTY for q == 0, like the reference
+    segs = [(0, 0, 0, mid_stop)]
+    i0, i1 = 1, 0
+    while True:
+        stop = True
+        if i1 < n1:
+            segs.append((1, i1, q, mid_stop))
+            i1 += 1
+            stop = False
+        if i0 < n0 - 1:
+            segs.append((0, i0, q, mid_stop))
+            i0 += 1
+            stop = False
+        if stop:
+            break
+    segs.append((0, n0 - 1, q, T))
+    return segs
+
+
+def compound(y0, y1):
+    """``compound(y0, y1)`` of test.py:46-84 for NumPy arrays or torch tensors (any device): (N, T, X) and
+    (N-1, T, X) -> (rows, X)."""
+    if y0.ndim != 3 or y1.ndim != 3 or y0.shape[1:] != y1.shape[1:]:
+        raise ValueError("compound: y0 (N, T, X) and y1 (M, T, X) must agree in T and X")
+    if y0.shape[0] < 1:
+        raise ValueError("compound: y0 needs at least one window")
+    src = (y0, y1)
+    parts = [src[s][i, a:b, :] for s, i, a, b in compound_segments(y0.shape[0], y1.shape[0], y0.shape[1])]
+    if al._is_tensor(y0):
+        import torch
+        return torch.cat(parts, dim=0)
+    return np.concatenate(parts, axis=0)
+
+
+def normalize_wav(y):
+    """``librosa.util.normalize(y, norm=inf)`` as applied by ``write_wav(..., norm=True)`` (test.py:177-179)."""
+    if al._is_tensor(y):
+        import torch
+        mag = y.abs().max() if y.numel() else torch.zeros((), dtype=y.dtype, device=y.device)
+        tiny = torch.finfo(y.dtype).tiny
+        return torch.where(mag < tiny, y, y / torch.clamp(mag, min=tiny))
+    y = np.asarray(y)
+    mag = np.max(np.abs(y)) if y.size else 0.0
+    tiny = np.finfo(y.dtype if np.issubdtype(y.dtype, np.floating) else np.float32).tiny
+    return y if mag < tiny else y / mag
+
+
+def render_windows(p0, p1, normalize=True, **power_to_wav_kw):
+    """Stitch window predictions of the power-dB head and render them: ``compound`` -> ``from_power_to_wav``
+    (-> peak normalisation), the sequence of test.py:140-179.  Device tensors stay on the device."""
+    P = compound(p0, p1)
+    y = al.from_power_to_wav(P, **power_to_wav_kw)
+    return normalize_wav(y) if normalize else y
