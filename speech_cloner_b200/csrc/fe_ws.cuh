@@ -33,6 +33,19 @@ constexpr int kWsEpiWarps = 7;                               // 8 FFT + 7 epilog
 constexpr int kWsEpiThreads = 32 * kWsEpiWarps;
 constexpr int kWsThreads = kWsFftThreads + kWsEpiThreads + 32;   // 512
 constexpr int kWsMaxTaps = 2048;                             // padded filterbank taps (floats) the kernel stages in shared memory
+// Optional register reallocation between the roles (setmaxnreg, per 4-warp group): the kernel launches with 128
+// registers per thread (16 warps = the whole register file); the two epilogue / prep warp groups give registers back
+// and the two FFT warp groups take them: 8*32*168 + 8*32*88 = 65536.  Measured (B200): no gain for the FFT role (it is
+// not register-ILP bound) and a slower epilogue (0.2096 -> 0.2124 ms), so it is off by default.
+#ifndef SC_WS_SETMAXNREG
+#define SC_WS_SETMAXNREG 0
+#endif
+#ifndef SC_WS_REG_FFT
+#define SC_WS_REG_FFT 168
+#endif
+#ifndef SC_WS_REG_EPI
+#define SC_WS_REG_EPI 88
+#endif
 constexpr int kWsRawSlots = 3;
 constexpr int kWsUnitSlots = 426;                            // complex slots per unit: 20 rows x 21 (+6): unit stride = 2 (mod 8) in 16-byte words
 constexpr int kWsDescRing = 8;
@@ -267,6 +280,9 @@ k_fe_pass_a_ws(const float* __restrict__ wav, const WsTile* __restrict__ tiles, 
 
     if (tid >= kWsFftThreads + kWsEpiThreads) {
         // =========================================== PREP warp ===========================================
+#if SC_WS_SETMAXNREG
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SC_WS_REG_EPI));
+#endif
         const int lane = tid & 31;
         const double c = prm.pre_emphasis;
         // stage(): publish the descriptor of local tile n and start the asynchronous copy of its raw samples into
@@ -385,6 +401,9 @@ k_fe_pass_a_ws(const float* __restrict__ wav, const WsTile* __restrict__ tiles, 
 
     if (tid < kWsFftThreads) {
         // =========================================== FFT warps ===========================================
+#if SC_WS_SETMAXNREG
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SC_WS_REG_FFT));
+#endif
         const int g = tid >> 7;                           // group 0 / 1: frames [12 g, 12 g + 12) of the tile
         const int lt = tid & 127;
         const int lane = tid & 31;
@@ -498,6 +517,9 @@ k_fe_pass_a_ws(const float* __restrict__ wav, const WsTile* __restrict__ tiles, 
     }
 
     // ============================================ EPILOGUE warps ============================================
+#if SC_WS_SETMAXNREG
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SC_WS_REG_EPI));
+#endif
     // Few warps do this work, so every phase is written for instruction-level parallelism: fixed trip counts
     // with predication (loads issue back to back), and a branch-light mel walk driven by per-bin records.
     {
