@@ -175,3 +175,35 @@ def test_preemphasis_pair(al):
     np.testing.assert_allclose(inv, oracle.calc_inv_preemphasis(y, 0.97), rtol=1e-12, atol=1e-13)
     # round trip through both filters recovers the float32 signal
     np.testing.assert_allclose(al.calc_inv_preemphasis(pe.astype(np.float32), 0.97), y, atol=2e-6)
+
+
+def test_long_utterance_many_tiles(al):
+    """One 60 s utterance: 500 tiles of the warp-specialised pass A and a depth-7 |y| tree in a single utterance."""
+    y = np.concatenate([synth.utterance(90 + i, 10.0) for i in range(6)]).astype(np.float32)
+    _check(al, y, "60 s", **HP)
+
+
+def test_tightly_packed_unaligned_offsets(al):
+    """The C ABI does not require 16-byte aligned utterance starts: packed offsets with odd lengths take the
+    4-byte staging path of pass A and the scalar pass B, and must give the same numbers as the aligned layout."""
+    import torch
+    lens = [16001, 9999, 4497, 31237]
+    wavs = [synth.utterance(60 + i, n / 16000.0)[:n] for i, n in enumerate(lens)]
+    kw = dict(sr=16000, n_fft=400, win_length=400, hop_length=80, n_mels=80, n_mfcc=40, window="hann", pre_emphasis=0.97,
+              mfcc_normaleze_first_mfcc=True, mfcc_norm_factor=0.01, calc_mfcc_derivate=True, M_dB_norm_factor=0.01,
+              P_dB_norm_factor=0.01, mean_abs_amp_norm=0.003, clip_output=True)
+    plan = al.DspPlan(**kw)
+    lay = al.FrontendLayout(lens, 80)
+    so, fo = [0], [0]
+    for n, t in zip(lens, lay.frames):
+        so.append(so[-1] + n)
+        fo.append(fo[-1] + t)
+    lay.sample_offsets, lay.frame_offsets = so, fo
+    lay.total_samples, lay.total_frames = so[-1], fo[-1]
+    lay.c_sample_offsets, lay.c_frame_offsets = al._lib.i64_array(so), al._lib.i64_array(fo)
+    dev = torch.from_numpy(np.concatenate(wavs)).cuda()
+    mfcc, mel, pdb = (x.cpu().numpy() for x in al.frontend_device(plan, dev, lay))
+    ref = al.calc_MFCC_input_batch(wavs, **HP)
+    for u, (o, t) in enumerate(zip(fo, lay.frames)):
+        for got, want, name in zip((mfcc[o:o + t], mel[o:o + t], pdb[o:o + t]), ref[u], ("MFCC", "M_dB", "P_dB")):
+            assert_close(got, want, rtol=1e-6, atol=2e-7, what=f"utt {u}/{name}")
