@@ -598,7 +598,7 @@ class FrontendPipeline:
     arrays; ``views()`` gives the per-utterance (MFCC, M_dB, P_dB) triples.
     """
 
-    def __init__(self, lengths: Sequence[int], n_chunks: int = 8, n_streams: int = 3, **plan_kw):
+    def __init__(self, lengths: Sequence[int], n_chunks: int = 8, n_streams: int = 3, ramp: bool = True, **plan_kw):
         torch = _require_cuda()
         self.torch = torch
         self.plans = [DspPlan(**plan_kw) for _ in range(n_streams)]
@@ -607,11 +607,23 @@ class FrontendPipeline:
         lay = self.layout
         n = len(lay.lengths)
         n_chunks = max(1, min(n_chunks, n))
-        # contiguous utterance groups with ~equal frame counts
-        bounds, acc, target = [0], 0, lay.total_frames / n_chunks
+        # contiguous utterance groups: the first ones are small and double in size (the download engine, which
+        # bounds the whole pass, starts after ~1/64 of the batch instead of after 1/n_chunks), the rest are equal
+        fracs, f = [], 1.0 / (8 * n_chunks) if ramp else 1.0 / n_chunks
+        while ramp and f < 1.0 / n_chunks and sum(fracs) + f < 1.0:
+            fracs.append(f)
+            f *= 2
+        rest = 1.0 - sum(fracs)
+        k = max(1, int(round(rest * n_chunks)))
+        fracs += [rest / k] * k
+        cuts, c = [], 0.0
+        for fr in fracs[:-1]:
+            c += fr
+            cuts.append(c * lay.total_frames)
+        bounds, acc = [0], 0
         for i, t in enumerate(lay.frames):
             acc += _align(t, 4)
-            if acc >= target * len(bounds) and len(bounds) < n_chunks and i + 1 < n:
+            if len(bounds) - 1 < len(cuts) and acc >= cuts[len(bounds) - 1] and i + 1 < n:
                 bounds.append(i + 1)
         bounds.append(n)
         self.chunks = []
