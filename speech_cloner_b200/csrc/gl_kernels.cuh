@@ -205,6 +205,8 @@ struct GlSmemP {
     float win_inv[kNfft];
     cxf slots[kFeUnits * kUnitSlots];
     float seg[kFeUnits * kGlSeg];
+    GlJob job[2];                       // descriptor of the staged tile: read from shared memory by the next iteration
+    int2 ent[2];
 };
 
 struct GlGeom {
@@ -242,6 +244,7 @@ k_gl_iter_persist(const GlJob* __restrict__ jobs, const int2* __restrict__ tile_
     auto stage = [&](int tile, int b) {
         const int2 e = tile_tab ? __ldg(tile_tab + tile) : make_int2(0, tile);   // no table: one job, tile = index
         const GlJob jb = jobs[e.x];
+        if (tid == 0) { sm.job[b] = jb; sm.ent[b] = e; }
         const GlGeom g = gl_geom(jb, e.y);
         const float* __restrict__ src = wav_in + jb.wav_in_off;
         const int q0 = g.span0 - kNfft / 2;
@@ -268,9 +271,9 @@ k_gl_iter_persist(const GlJob* __restrict__ jobs, const int2* __restrict__ tile_
     __syncthreads();
 #pragma unroll 1
     for (; tile < n_tiles; tile += gridDim.x, b ^= 1) {
+        const int2 e = sm.ent[b];                     // written by stage() one iteration (and one barrier) ago
+        const GlJob job = sm.job[b];
         if (tile + (int)gridDim.x < n_tiles) stage(tile + gridDim.x, b ^ 1);
-        const int2 e = tile_tab ? __ldg(tile_tab + tile) : make_int2(0, tile);
-        const GlJob job = jobs[e.x];
         const GlGeom g = gl_geom(job, e.y);
         const int T = g.T, Lw = g.Lw, out_first = g.out_first, out_end = g.out_end, t0 = g.t0, span0 = g.span0;
         const float* __restrict__ span = sm.span[b];
