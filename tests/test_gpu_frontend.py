@@ -207,3 +207,23 @@ def test_tightly_packed_unaligned_offsets(al):
     for u, (o, t) in enumerate(zip(fo, lay.frames)):
         for got, want, name in zip((mfcc[o:o + t], mel[o:o + t], pdb[o:o + t]), ref[u], ("MFCC", "M_dB", "P_dB")):
             assert_close(got, want, rtol=1e-6, atol=2e-7, what=f"utt {u}/{name}")
+
+
+@pytest.mark.parametrize("n_chunks,n_streams,ramp", [(8, 3, True), (3, 2, False), (64, 4, True), (1, 1, True)])
+def test_host_pipeline_equals_batch_call(al, n_chunks, n_streams, ramp):
+    """FrontendPipeline (bench.py's e2e path: pinned H2D -> kernels -> pinned D2H over several streams, ramped chunk
+    sizes) must return exactly what one ragged batch call returns, for every chunking."""
+    lens = [16000, 8001, 24000, 4497, 12345, 400, 31999, 16000, 7777, 20000, 9600, 480]
+    wavs = [synth.utterance(300 + i, n / 16000.0)[:n] for i, n in enumerate(lens)]
+    kw = dict(sr=16000, n_fft=400, win_length=400, hop_length=80, n_mels=80, n_mfcc=40, window="hann", pre_emphasis=0.97,
+              mfcc_normaleze_first_mfcc=True, mfcc_norm_factor=0.01, calc_mfcc_derivate=True, M_dB_norm_factor=0.01,
+              P_dB_norm_factor=0.01, mean_abs_amp_norm=0.003, clip_output=True)
+    pipe = al.FrontendPipeline(lens, n_chunks=n_chunks, n_streams=n_streams, ramp=ramp, **kw)
+    assert sum(b - a for a, b, *_ in pipe.chunks) == len(lens)
+    pipe.load(wavs)
+    pipe.run()
+    pipe.run()                                              # buffers are reused: a second pass must give the same
+    want = al.calc_MFCC_input_batch(wavs, **HP)
+    for got, ref in zip(pipe.views(), want):
+        for g, r in zip(got, ref):
+            np.testing.assert_array_equal(g, r)
