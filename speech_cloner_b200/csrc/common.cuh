@@ -91,11 +91,20 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // 10*log10(x) for x > 0 through the MUFU log2 unit: abs error ~2e-5 dB, three orders below the
 // 1e-3 dB that the 1e-5 output tolerance allows after the 0.01 scale (audio_lib.py:231).
+// Where the raw power dB (audio_lib.py:157 before the top_db clip) is computed: 1 = pass A stores |X|^2 and pass B takes
+// the logarithm while it clips and shifts (pass B is HBM-bound and has issue slots to spare, pass A has not);
+// 0 = pass A stores dB.  Same operations on the same values either way: results are bit-identical.
+#ifndef SC_DB_IN_PASS_B
+#define SC_DB_IN_PASS_B 1
+#endif
 // Every caller clamps x to >= 1e-10, so the denormal pre-scaling that __log2f() adds around the MUFU is dropped.
 __device__ __forceinline__ float db10(float x) {
     float l;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
     return 3.0102999566398120f * l;
 }
+// value pass A stores for a power p / value pass B reads back as raw dB
+__device__ __forceinline__ float pdb_store(float p) { return SC_DB_IN_PASS_B ? p : db10(fmaxf(p, 1e-10f)); }
+__device__ __forceinline__ float pdb_load(float v) { return SC_DB_IN_PASS_B ? db10(fmaxf(v, 1e-10f)) : v; }
 
 }  // namespace scdsp

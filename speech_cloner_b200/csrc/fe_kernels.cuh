@@ -477,15 +477,14 @@ __device__ __forceinline__ void fe_epilogue_a(const float* __restrict__ power, i
                 const float4 p = p4[e];
                 p_max = fmaxf(fmaxf(p_max, fmaxf(p.x, p.y)), fmaxf(p.z, p.w));
                 p_min = fminf(fminf(p_min, fminf(p.x, p.y)), fminf(p.z, p.w));
-                d4[e] = make_float4(db10(fmaxf(p.x, 1e-10f)), db10(fmaxf(p.y, 1e-10f)), db10(fmaxf(p.z, 1e-10f)),
-                                    db10(fmaxf(p.w, 1e-10f)));
+                d4[e] = make_float4(pdb_store(p.x), pdb_store(p.y), pdb_store(p.z), pdb_store(p.w));
             }
         } else {
             for (int e = tid; e < n; e += THREADS) {
                 const float p = power[e];
                 p_max = fmaxf(p_max, p);
                 p_min = fminf(p_min, p);
-                pdb_dst[e] = db10(fmaxf(p, 1e-10f));
+                pdb_dst[e] = pdb_store(p);
             }
         }
     }
@@ -915,10 +914,10 @@ k_fe_pass_b(Ragged rg, FeTables tb, FeParams prm, const UttStat* __restrict__ st
             float4* __restrict__ p4 = reinterpret_cast<float4*>(p);
             const int n4 = n >> 2;
             auto fix = [&](float4 v) {
-                v.x = fminf(fmaxf(mul * (fmaxf(v.x, floor_db) - sub), -cl), cl);
-                v.y = fminf(fmaxf(mul * (fmaxf(v.y, floor_db) - sub), -cl), cl);
-                v.z = fminf(fmaxf(mul * (fmaxf(v.z, floor_db) - sub), -cl), cl);
-                v.w = fminf(fmaxf(mul * (fmaxf(v.w, floor_db) - sub), -cl), cl);
+                v.x = fminf(fmaxf(mul * (fmaxf(pdb_load(v.x), floor_db) - sub), -cl), cl);
+                v.y = fminf(fmaxf(mul * (fmaxf(pdb_load(v.y), floor_db) - sub), -cl), cl);
+                v.z = fminf(fmaxf(mul * (fmaxf(pdb_load(v.z), floor_db) - sub), -cl), cl);
+                v.w = fminf(fmaxf(mul * (fmaxf(pdb_load(v.w), floor_db) - sub), -cl), cl);
                 return v;
             };
             // 4 independent 16-byte loads in flight per thread (the pass is latency-, not compute-bound)
@@ -932,7 +931,7 @@ k_fe_pass_b(Ragged rg, FeTables tb, FeParams prm, const UttStat* __restrict__ st
             head = n4 << 2;
         }
         for (int e = head + tid; e < n; e += kFbThreads)
-            p[e] = fminf(fmaxf(mul * (fmaxf(p[e], floor_db) - sub), -cl), cl);
+            p[e] = fminf(fmaxf(mul * (fmaxf(pdb_load(p[e]), floor_db) - sub), -cl), cl);
     }
 
     // ---- mel dB rows t0-1 .. t0+nfr (halo for the delta): clip, write the normalised rows, build (s, d)
@@ -1201,7 +1200,7 @@ k_fe_pass_b2(Ragged rg, FeTables tb, FeParams prm, const UttStat* __restrict__ s
         const float sub = prm.shift_p ? lo : 0.0f;
         const float mul = prm.shift_p ? prm.p_db_norm_factor : 1.0f;
         auto fix = [&](float4 v) {
-            v.x = fmaxf(v.x, floor_db); v.y = fmaxf(v.y, floor_db); v.z = fmaxf(v.z, floor_db); v.w = fmaxf(v.w, floor_db);
+            v.x = fmaxf(pdb_load(v.x), floor_db); v.y = fmaxf(pdb_load(v.y), floor_db); v.z = fmaxf(pdb_load(v.z), floor_db); v.w = fmaxf(pdb_load(v.w), floor_db);
             return fb2_norm(v, sub, mul, cl);
         };
 #pragma unroll
@@ -1211,7 +1210,7 @@ k_fe_pass_b2(Ragged rg, FeTables tb, FeParams prm, const UttStat* __restrict__ s
         }
         float* __restrict__ p = pdb + row0 * n_bins;
         for (int q = (n4 << 2) + tid; q < n_pdb; q += kFbThreads)
-            p[q] = fminf(fmaxf(mul * (fmaxf(p[q], floor_db) - sub), -cl), cl);
+            p[q] = fminf(fmaxf(mul * (fmaxf(pdb_load(p[q]), floor_db) - sub), -cl), cl);
     }
     __syncthreads();
 
@@ -1416,13 +1415,13 @@ k_fe_pass_b3(const B3Tile* __restrict__ tiles, int total_tiles, FeTables tb, FeP
                 const int e = tid + it * kB3Threads;
                 if (e < n4) {
                     float4 v = pv[it];
-                    v.x = fmaxf(v.x, floor_db); v.y = fmaxf(v.y, floor_db); v.z = fmaxf(v.z, floor_db); v.w = fmaxf(v.w, floor_db);
+                    v.x = fmaxf(pdb_load(v.x), floor_db); v.y = fmaxf(pdb_load(v.y), floor_db); v.z = fmaxf(pdb_load(v.z), floor_db); v.w = fmaxf(pdb_load(v.w), floor_db);
                     p4[e] = fb2_norm(v, sub, mul, cl);
                 }
             }
             float* __restrict__ p = pdb + row0 * kBins;
             for (int q = (n4 << 2) + tid; q < n_pdb; q += kB3Threads)
-                p[q] = fminf(fmaxf(mul * (fmaxf(p[q], floor_db) - sub), -cl), cl);
+                p[q] = fminf(fmaxf(mul * (fmaxf(pdb_load(p[q]), floor_db) - sub), -cl), cl);
         }
         __syncthreads();                       // sd_s complete (and the previous tile's cc_s fully read)
         if (tile + (int)gridDim.x < total_tiles) load(tile + gridDim.x);      // next tile in flight during the DCT

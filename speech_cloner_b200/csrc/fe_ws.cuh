@@ -564,8 +564,7 @@ k_fe_pass_a_ws(const float* __restrict__ wav, const WsTile* __restrict__ tiles, 
                             const float4 q = p[it];
                             p_max = fmaxf(fmaxf(p_max, fmaxf(q.x, q.y)), fmaxf(q.z, q.w));
                             p_min = fminf(fminf(p_min, fminf(q.x, q.y)), fminf(q.z, q.w));
-                            d4[e] = make_float4(db10(fmaxf(q.x, 1e-10f)), db10(fmaxf(q.y, 1e-10f)),
-                                                db10(fmaxf(q.z, 1e-10f)), db10(fmaxf(q.w, 1e-10f)));
+                            d4[e] = make_float4(pdb_store(q.x), pdb_store(q.y), pdb_store(q.z), pdb_store(q.w));
                         }
                     }
                     head = n4 << 2;
@@ -574,7 +573,7 @@ k_fe_pass_a_ws(const float* __restrict__ wav, const WsTile* __restrict__ tiles, 
                     const float p = P[e];
                     p_max = fmaxf(p_max, p);
                     p_min = fminf(p_min, p);
-                    dst[e] = db10(fmaxf(p, 1e-10f));
+                    dst[e] = pdb_store(p);
                 }
             }
 #ifdef SC_WS_DEBUG
