@@ -536,6 +536,10 @@ k_fe_pass_a_ws(const float* __restrict__ wav, const WsTile* __restrict__ tiles, 
 #ifdef SC_WS_DEBUG
             const long long t_a = clock64();
 #endif
+#ifdef SC_WS_NO_EPI      // experiment: how fast is the prep + FFT pipeline alone?
+            mbar_arrive(&sm.bar_pw_empty[b]);
+            continue;
+#endif
             const WsTile t = sm.desc[i % kWsDescRing];
             const float* __restrict__ P = sm.power[b];
             float* __restrict__ ms = mel_s + b * (kWsFrames * mel_ld);
