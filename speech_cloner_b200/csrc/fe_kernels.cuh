@@ -1285,19 +1285,6 @@ struct B3Tile {
     int32_t u, t0, T, pad;
 };
 
-__global__ void k_b3_tiles(Ragged rg, int total_tiles, B3Tile* __restrict__ out) {
-    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tile >= total_tiles) return;
-    const int u = find_utt(rg.tile_prefix, rg.n_utts, tile);
-    B3Tile t;
-    t.u = u;
-    t.t0 = (tile - rg.tile_prefix[u]) * kB3Frames;
-    t.T = rg.frame_cnt[u];
-    t.frame_off = rg.frame_off[u];
-    t.pad = 0;
-    out[tile] = t;
-}
-
 // One (row, coefficient group) DCT task: 4 even + 4 odd coefficients, weights as broadcast 128-bit shared loads.
 __device__ __forceinline__ void b3_dct_group(const float4* __restrict__ e4, const float4* __restrict__ o4,
                                              const float2* __restrict__ x, bool first_group, float c00, float sc,

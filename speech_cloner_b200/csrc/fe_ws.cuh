@@ -1,7 +1,7 @@
 // Warp-specialised persistent pass A of the front-end (fast path: n_fft = 400, hop = 80).
 //
 // Same arithmetic as k_fe_pass_a (audio_lib.py:125-172: gain -> pre-emphasis -> reflect pad -> window
-// -> rFFT-400 -> |X|^2 -> raw power dB, sparse Slaney mel -> raw mel dB, utterance max / min), but the
+// -> rFFT-400 -> |X|^2 -> raw power (dB taken in pass B), sparse Slaney mel -> raw mel dB, utterance max / min), but the
 // three kinds of work run on different warps of one CTA per SM and overlap tile against tile:
 //
 //   warp 15      PREP      stages the raw samples of tile i+2 with one TMA bulk copy (cp.async.bulk ->
@@ -11,9 +11,10 @@
 //   warps 0-7    FFT       two independent groups of 6 units x 20 threads (12 frames each): windowed
 //                          real FFT-400 in float64, |X|^2 into a double-buffered power tile.  Only
 //                          FP64-pipe and shared-memory work: no global access, no MUFU
-//   warps 8-14   EPILOGUE  power dB + coalesced 128-bit stores, the sparse mel filterbank with lane = frame
-//                          (one band at a time, 4 taps per step, weights as broadcast 128-bit loads), raw mel
-//                          dB, utterance max / min.  FP32 / MUFU / LSU work that hides under the FFT warps
+//   warps 8-14   EPILOGUE  |X|^2 out with coalesced 128-bit stores (pass B takes the logarithm), the sparse mel
+//                          filterbank with lane = frame (two bands per step, 4 taps per block, weights as broadcast
+//                          128-bit loads), raw mel dB, utterance max / min.  FP32 / MUFU / LSU work that runs beside
+//                          the FFT warps
 //
 // Hand-offs are mbarriers (full / empty pairs, parity from the tile counter), the two FFT groups
 // use one named barrier each, so no warp ever waits for a role it does not depend on.
@@ -50,7 +51,7 @@ constexpr int kWsRawSlots = 3;
 constexpr int kWsUnitSlots = 426;                            // complex slots per unit: 20 rows x 21 (+6): unit stride = 2 (mod 8) in 16-byte words
 constexpr int kWsDescRing = 8;
 
-// one record per tile, written by k_ws_tiles
+// one record per tile, written by k_fe_setup
 struct WsTile {
     int64_t sample_off;     // first sample of the utterance in the packed buffer
     int64_t L;              // utterance length
@@ -70,25 +71,9 @@ struct WsMelParam {
     int32_t n_taps;                       // floats in the weight table (multiple of 8, <= kWsMaxTaps)
 };
 
-__global__ void k_ws_tiles(Ragged rg, int total_tiles, WsTile* __restrict__ out) {
-    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tile >= total_tiles) return;
-    const int u = find_utt(rg.tile_prefix, rg.n_utts, tile);
-    WsTile t;
-    t.u = u;
-    t.t0 = (tile - rg.tile_prefix[u]) * kWsFrames;
-    t.nfr = min(kWsFrames, rg.frame_cnt[u] - t.t0);
-    t.L = rg.sample_len[u];
-    t.sample_off = rg.sample_off[u];
-    t.frame_row = rg.frame_off[u] + t.t0;
-    const int64_t q0 = (int64_t)t.t0 * kHop - kNfft / 2;
-    t.edge = !(q0 - 4 >= 0 && q0 + kWsSpan + 4 <= t.L);
-    out[tile] = t;
-}
-
 // One launch that writes every per-call table of the fast front-end path: the sub-tree records of the |y| sum,
-// the tiles of k_fe_pass_a_ws and the tiles of k_fe_pass_b3, and resets the per-utterance statistics is left to
-// k_gain_finalize.  Thread id space: [0, n_abs) | [n_abs, n_abs + n_ws) | [.., + n_b3).
+// the tiles of k_fe_pass_a_ws and the tiles of k_fe_pass_b3 (the per-utterance statistics are reset by
+// k_gain_finalize).  Thread id space: [0, n_abs) | [n_abs, n_abs + n_ws) | [.., + n_b3).
 struct SetupArgs {
     const int32_t* pre_abs; const int32_t* pre_ws; const int32_t* pre_b3;
     const int64_t* heap_off;
