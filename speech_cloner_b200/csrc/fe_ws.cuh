@@ -78,6 +78,7 @@ struct SetupArgs {
     const int32_t* pre_abs; const int32_t* pre_ws; const int32_t* pre_b3;
     const int64_t* heap_off;
     int32_t n_abs, n_ws, n_b3;
+    int32_t ws_frames;            // frames per pass A tile: kWsFrames (k_fe_pass_a_ws) or kSpFrames (k_fe_fft)
     AbsRec* abs_out; WsTile* ws_out; B3Tile* b3_out;
 };
 __global__ void k_fe_setup(Ragged rg, SetupArgs sa) {
@@ -105,13 +106,13 @@ __global__ void k_fe_setup(Ragged rg, SetupArgs sa) {
         const int u = find_utt(sa.pre_ws, rg.n_utts, i);
         WsTile t;
         t.u = u;
-        t.t0 = (i - sa.pre_ws[u]) * kWsFrames;
-        t.nfr = min(kWsFrames, rg.frame_cnt[u] - t.t0);
+        t.t0 = (i - sa.pre_ws[u]) * sa.ws_frames;
+        t.nfr = min(sa.ws_frames, rg.frame_cnt[u] - t.t0);
         t.L = rg.sample_len[u];
         t.sample_off = rg.sample_off[u];
         t.frame_row = rg.frame_off[u] + t.t0;
         const int64_t q0 = (int64_t)t.t0 * kHop - kNfft / 2;
-        t.edge = !(q0 - 4 >= 0 && q0 + kWsSpan + 4 <= t.L);
+        t.edge = !(q0 - 4 >= 0 && q0 + (kHop * (sa.ws_frames - 1) + kNfft) + 4 <= t.L);
         sa.ws_out[i] = t;
         return;
     }

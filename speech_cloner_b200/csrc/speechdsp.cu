@@ -12,6 +12,7 @@
 
 #include "fe_kernels.cuh"
 #include "fe_ws.cuh"
+#include "fe_split.cuh"
 #include "gl_kernels.cuh"
 #include "generic_kernels.cuh"
 #include "phn_kernels.cuh"
@@ -128,6 +129,7 @@ struct sc_plan {
     const float* ws_wt = nullptr;   // padded filterbank weights
     bool use_b2 = true;      // vector form of pass B (env SC_FE_B2=0 selects the scalar kernel)
     bool use_b3 = false;     // compile-time specialised pass B (80 mels, 40 MFCC, 201 bins; env SC_FE_B3=0 disables)
+    bool use_split = false;  // pass A as FFT-only kernel + streaming mel kernel (env SC_FE_SPLIT=1)
     bool use_ws = true;      // warp-specialised pass A (env SC_FE_WS=0 selects the older persistent kernel)
     int64_t fe_group_frames = int64_t(1) << 60;   // frames per front-end group (env SC_FE_GROUP_FRAMES); measured: grouping for L2 residency only adds launch latency, so off by default
 };
@@ -344,6 +346,7 @@ extern "C" int sc_plan_create(const sc_params* p, sc_plan** out) {
     if (ws_wt.empty()) ws_wt.push_back(0.f);
     if (const char* e = getenv("SC_FE_WS")) pl->use_ws = pl->use_ws && atoi(e) != 0;
     if (const char* e = getenv("SC_FE_B2")) pl->use_b2 = atoi(e) != 0;
+    if (const char* e = getenv("SC_FE_SPLIT")) pl->use_split = atoi(e) != 0;
     // librosa.filters.dct (audio_lib.py:176): row 0 = 1/sqrt(N), row q = sqrt(2/N) cos(q (2n+1) pi / 2N),
     // split into even / odd rows over the first half of the inputs (see k_fe_pass_b)
     const FbLayout fbl = fb_layout(p->n_mels, p->n_mfcc);
@@ -462,18 +465,20 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
                           float* mfcc, float* mel, float* pdb, const int64_t* foff, cudaStream_t st, int group) {
     const int hop = pl->prm.hop_length;
     std::vector<int64_t> slen(slen_in, slen_in + n), so(soff, soff + n), fo(foff, foff + n);
-    std::vector<int32_t> fcnt(n), pre_abs(n + 1), pre_a(n + 1), pre_b(n + 1), pre_b3(n + 1), pre_int(n + 1), ifirst(n), icount(n);
+    std::vector<int32_t> fcnt(n), pre_abs(n + 1), pre_a(n + 1), pre_b(n + 1), pre_b3(n + 1), pre_int(n + 1), pre_mel(n + 1), ifirst(n), icount(n);
     std::vector<int64_t> heap_off(n + 1);
     int64_t total_frames_span = 0;
     constexpr int kPU = 8;                         // units per CTA of the fast pass-A kernels (16 frames per tile)
     const bool ws = pl->fast && pl->use_ws;        // long utterances: warp-specialised kernel, 24-frame tiles
+    const bool split = ws && pl->use_split && SC_DB_IN_PASS_B;   // ... or the FFT-only + mel kernel pair, 12-frame tiles
+    const int ws_frames = split ? kSpFrames : kWsFrames;
     const int a_frames = pl->fast ? 2 * kPU : kGenFeFrames;
     for (int u = 0; u < n; ++u) {
         const int64_t T = 1 + slen[u] / hop;
         fcnt[u] = (int32_t)T;
         if (fo[u] + T > total_frames_span) total_frames_span = fo[u] + T;
     }
-    pre_abs[0] = pre_a[0] = pre_b[0] = pre_b3[0] = pre_int[0] = 0;
+    pre_abs[0] = pre_a[0] = pre_b[0] = pre_b3[0] = pre_int[0] = pre_mel[0] = 0;
     heap_off[0] = 0;
     for (int u = 0; u < n; ++u) {
         const int64_t ta = pre_abs[u] + (int64_t(1) << abs_depth(slen[u]));
@@ -482,17 +487,19 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
         // first / last tiles gather their reflect padding); shorter utterances, whose padding could wrap more
         // than once, use the plain kernel
         int64_t n_tiles_u = (fcnt[u] + a_frames - 1) / a_frames, k_lo = 0, k_hi = -1;
-        int64_t n_int = 0;
+        int64_t n_int = 0, n_mel = 0;
         if (pl->fast) {
-            const int p_frames = ws ? kWsFrames : a_frames;                   // tile of the persistent kernel
+            const int p_frames = ws ? ws_frames : a_frames;                   // tile of the persistent kernel
             const int64_t span = (int64_t)kHop * (p_frames - 1) + kNfft;
             if (slen[u] >= 2 * span + 16) {
                 k_hi = n_tiles_u - 1;
-                n_int = ws ? (fcnt[u] + kWsFrames - 1) / kWsFrames : n_tiles_u;
+                n_int = ws ? (fcnt[u] + ws_frames - 1) / ws_frames : n_tiles_u;
+                n_mel = (fcnt[u] + kMelFrames - 1) / kMelFrames;
             }
         }
         ifirst[u] = (int32_t)k_lo; icount[u] = (int32_t)(k_hi >= k_lo ? k_hi - k_lo + 1 : 0);
         pre_int[u + 1] = (int32_t)(pre_int[u] + n_int);
+        pre_mel[u + 1] = (int32_t)(pre_mel[u] + n_mel);
         const int64_t tb = pre_a[u] + n_tiles_u - icount[u];                  // edge (or all generic-path) tiles
         const int64_t tc = pre_b[u] + (fcnt[u] + kFbFrames - 1) / kFbFrames;
         if (ta > INT32_MAX || tb > INT32_MAX) return fail(SC_ERR_INVALID, "sc_frontend_batch: batch too large");
@@ -504,7 +511,7 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
     const size_t o_pabs = b.add(pre_abs), o_pa = b.add(pre_a), o_pb = b.add(pre_b), o_heap = b.add(heap_off);
     const size_t o_pint = b.add(pre_int), o_if = b.add(ifirst), o_ic = b.add(icount);
     const size_t o_arec = b.add(abs_recs(pre_abs, n));
-    const size_t o_pb3 = b.add(pre_b3);
+    const size_t o_pb3 = b.add(pre_b3), o_pmel = b.add(pre_mel);
     if (int rc = upload_blob(pl, b, st)) return rc;
 
     // workspace: stats | abs partials | raw mel
@@ -541,6 +548,7 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
         sa.heap_off = at<int64_t>(pl, o_heap);
         sa.n_abs = (fp.use_gain && abs_variant() == 4) ? pre_abs[n] : 0;
         sa.n_ws = ws ? pre_int[n] : 0;
+        sa.ws_frames = ws_frames;
         sa.n_b3 = b3 ? pre_b3[n] : 0;
         sa.abs_out = reinterpret_cast<AbsRec*>(wb + w_arec);
         sa.ws_out = reinterpret_cast<WsTile*>(wb + w_tiles);
@@ -580,7 +588,28 @@ static int frontend_range(sc_plan* pl, const float* wav, const int64_t* soff, co
         }
         const size_t mel_bytes = sizeof(float) * 2 * kPU * (pl->prm.n_mels + 1);
         rg.int_first = at<int32_t>(pl, o_if); rg.int_count = at<int32_t>(pl, o_ic);
-        if (ws && pre_int[n] > 0) {
+        if (split && pre_int[n] > 0) {
+            // FFT-only persistent kernel (three prep + FFT pipelines per SM) followed by the streaming mel kernel
+            static bool sp_attr = false;
+            if (!sp_attr) {
+                SC_CUDA(cudaFuncSetAttribute(k_fe_fft<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpSmem<float>)));
+                SC_CUDA(cudaFuncSetAttribute(k_fe_fft<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpSmem<double>)));
+                SC_CUDA(cudaFuncSetAttribute(k_fe_mel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_mel_smem_bytes(kMaxMels)));
+                sp_attr = true;
+            }
+            WsTile* tiles = reinterpret_cast<WsTile*>(wb + w_tiles);
+            const int need = (pre_int[n] + kSpPipes - 1) / kSpPipes;
+            const int grid = need < n_sm ? need : n_sm;
+            if (pl->fp32_fft)
+                k_fe_fft<float><<<grid, kSpThreads, sizeof(SpSmem<float>), st>>>(wav, tiles, pre_int[n], tb, fp, stat, pdb);
+            else
+                k_fe_fft<double><<<grid, kSpThreads, sizeof(SpSmem<double>), st>>>(wav, tiles, pre_int[n], tb, fp, stat, pdb);
+            SC_LAUNCHED();
+            rg.tile_prefix = at<int32_t>(pl, o_pmel);
+            k_fe_mel<<<pre_mel[n], kMelThreads, fe_mel_smem_bytes(pl->prm.n_mels), st>>>(rg, stat, pdb, mel_raw, pl->ws_brec,
+                                                                                         pl->ws_wt, pl->ws_mel);
+            SC_LAUNCHED();
+        } else if (ws && pre_int[n] > 0) {
             // warp-specialised persistent kernel (fe_ws.cuh): one CTA per SM
             static bool ws_attr = false;
             const size_t mel_s_bytes = sizeof(float) * 2 * kWsFrames * (pl->prm.n_mels | 1);
