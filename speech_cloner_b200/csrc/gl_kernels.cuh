@@ -12,6 +12,9 @@
 
 namespace scdsp {
 
+#ifndef SC_GL_SPLIT_TASKS
+#define SC_GL_SPLIT_TASKS 0      // 1: packed columns c = 0 on warp 0 and c = 10 on warp 1 (each next to one-frame columns)
+#endif
 constexpr int kGlFrames = 32;                          // frames per tile (16 units x 2)
 constexpr int kGlOutHops = kGlFrames - 4;              // complete hops per tile
 constexpr int kGlOut = kGlOutHops * kHop;              // 2240 output samples per tile
@@ -304,7 +307,7 @@ k_gl_iter_persist(const GlJob* __restrict__ jobs, const int2* __restrict__ tile_
         {
             // step-2 task of this thread (packed columns on warp 0, see step2_task) and its unit's two frames
             int u2, c2;
-            step2_task<false>(tid, kFeUnits, u2, c2);
+            step2_task<SC_GL_SPLIT_TASKS != 0>(tid, kFeUnits, u2, c2);
             const int ga = t0 + 2 * u2, gb = ga + 1;
             const bool wa = ga >= job.f_lo && ga < job.f_lo + job.f_cnt && ga < T;
             const bool wb = gb >= job.f_lo && gb < job.f_lo + job.f_cnt && gb < T;
