@@ -1305,6 +1305,17 @@ __device__ __forceinline__ void b3_dct_group(const float4* __restrict__ e4, cons
 
 // Persistent: a CTA keeps the DCT basis in shared memory for its whole life and loads tile i+1 into registers
 // while the DCT and the MFCC output of tile i run, so DRAM latency is hidden behind arithmetic.
+// cache hints of pass B3: every byte is read once and written once (SC_B3_STREAM=1: ld.global.cs / st.global.cs)
+#ifndef SC_B3_STREAM
+#define SC_B3_STREAM 0
+#endif
+#if SC_B3_STREAM
+#define B3_LD(p) __ldcs(p)
+#define B3_ST(p, v) __stcs(p, v)
+#else
+#define B3_LD(p) (*(p))
+#define B3_ST(p, v) (*(p) = (v))
+#endif
 __global__ void __launch_bounds__(kB3Threads, 3)
 k_fe_pass_b3(const B3Tile* __restrict__ tiles, int total_tiles, FeTables tb, FeParams prm, const UttStat* __restrict__ stat,
              const float* __restrict__ mel_raw, float* __restrict__ pdb, float* __restrict__ mel_out,
@@ -1333,7 +1344,7 @@ k_fe_pass_b3(const B3Tile* __restrict__ tiles, int total_tiles, FeTables tb, FeP
 #pragma unroll
         for (int it = 0; it < kPdbIt; ++it) {
             const int e = tid + it * kB3Threads;
-            if (e < n4) pv[it] = p4[e];
+            if (e < n4) pv[it] = B3_LD(p4 + e);
         }
         const float4* __restrict__ msrc = reinterpret_cast<const float4*>(mel_raw + tl.frame_off * kB3Mels);
 #pragma unroll
@@ -1342,8 +1353,8 @@ k_fe_pass_b3(const B3Tile* __restrict__ tiles, int total_tiles, FeTables tb, FeP
             const int r = task / kQRow, m4 = task - r * kQRow;
             const int t = tl.t0 - 1 + r;
             if (r < nfr + 2 && t >= 0 && t < tl.T) {
-                a[it] = __ldg(msrc + (int64_t)t * kRow4 + m4);
-                b[it] = __ldg(msrc + (int64_t)t * kRow4 + (kRow4 - 1 - m4));
+                a[it] = B3_LD(msrc + (int64_t)t * kRow4 + m4);
+                b[it] = B3_LD(msrc + (int64_t)t * kRow4 + (kRow4 - 1 - m4));
             }
         }
     };
@@ -1375,8 +1386,8 @@ k_fe_pass_b3(const B3Tile* __restrict__ tiles, int total_tiles, FeTables tb, FeP
                     xa.x = fmaxf(xa.x, m_floor); xa.y = fmaxf(xa.y, m_floor); xa.z = fmaxf(xa.z, m_floor); xa.w = fmaxf(xa.w, m_floor);
                     xb.x = fmaxf(xb.x, m_floor); xb.y = fmaxf(xb.y, m_floor); xb.z = fmaxf(xb.z, m_floor); xb.w = fmaxf(xb.w, m_floor);
                     if (r >= 1 && r <= nfr) {
-                        dst[(int64_t)t * kRow4 + m4] = fb2_norm(xa, sub, mul, cl);
-                        dst[(int64_t)t * kRow4 + (kRow4 - 1 - m4)] = fb2_norm(xb, sub, mul, cl);
+                        B3_ST(dst + (int64_t)t * kRow4 + m4, fb2_norm(xa, sub, mul, cl));
+                        B3_ST(dst + (int64_t)t * kRow4 + (kRow4 - 1 - m4), fb2_norm(xb, sub, mul, cl));
                     }
                     sd[0] = make_float2(xa.x + xb.w, xa.x - xb.w);
                     sd[1] = make_float2(xa.y + xb.z, xa.y - xb.z);
@@ -1403,7 +1414,7 @@ k_fe_pass_b3(const B3Tile* __restrict__ tiles, int total_tiles, FeTables tb, FeP
                 if (e < n4) {
                     float4 v = pv[it];
                     v.x = fmaxf(pdb_load(v.x), floor_db); v.y = fmaxf(pdb_load(v.y), floor_db); v.z = fmaxf(pdb_load(v.z), floor_db); v.w = fmaxf(pdb_load(v.w), floor_db);
-                    p4[e] = fb2_norm(v, sub, mul, cl);
+                    B3_ST(p4 + e, fb2_norm(v, sub, mul, cl));
                 }
             }
             float* __restrict__ p = pdb + row0 * kBins;
@@ -1429,8 +1440,8 @@ k_fe_pass_b3(const B3Tile* __restrict__ tiles, int total_tiles, FeTables tb, FeP
                 const int r = task / kQ, q4 = task - r * kQ;
                 const int t = t0 + r;
                 const float4 c = *reinterpret_cast<const float4*>(cc_s + (r + 1) * kB3CcLd + 4 * q4);
-                dst[r * width4 + q4] = make_float4(fminf(fmaxf(c.x, -cl), cl), fminf(fmaxf(c.y, -cl), cl),
-                                                   fminf(fmaxf(c.z, -cl), cl), fminf(fmaxf(c.w, -cl), cl));
+                B3_ST(dst + r * width4 + q4, make_float4(fminf(fmaxf(c.x, -cl), cl), fminf(fmaxf(c.y, -cl), cl),
+                                                         fminf(fmaxf(c.z, -cl), cl), fminf(fmaxf(c.w, -cl), cl)));
                 if (prm.use_delta) {
                     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (t != 0 && t != T - 1) {
@@ -1439,7 +1450,7 @@ k_fe_pass_b3(const B3Tile* __restrict__ tiles, int total_tiles, FeTables tb, FeP
                         d = make_float4(fminf(fmaxf(2.0f * (up.x - dn.x), -cl), cl), fminf(fmaxf(2.0f * (up.y - dn.y), -cl), cl),
                                         fminf(fmaxf(2.0f * (up.z - dn.z), -cl), cl), fminf(fmaxf(2.0f * (up.w - dn.w), -cl), cl));
                     }
-                    dst[r * width4 + kQ + q4] = d;
+                    B3_ST(dst + r * width4 + kQ + q4, d);
                 }
             }
         }
