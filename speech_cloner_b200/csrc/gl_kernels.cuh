@@ -181,17 +181,30 @@ k_gl_iter(const GlJob* __restrict__ jobs, int n_jobs, const int32_t* __restrict_
         float* __restrict__ dst = wav_out + job.wav_out_off;
         // every output sample of an interior tile is covered by all 5 frames: periodic 1 / sum-square
         const bool steady = t0 >= 0 && t0 + kGlFrames <= T;
-        for (int i = tid; i < kGlOut; i += kFeThreads) {
-            const int l = 320 + i;                                  // local padded offset in the tile
+        // same static form as k_gl_iter_persist (units uh-2, uh-1, uh at offsets r+320, r+160, r; ascending-unit sums)
+        static_assert(kGlOut == 7 * kFeThreads && kFeThreads == 4 * kHop && kGlSeg == 6 * kHop, "tile geometry");
+        const int h = tid >= 2 * kHop ? 1 : 0;
+        const int r = tid - 2 * kHop * h;
+        const float* __restrict__ sg = seg + h * kGlSeg + r;
+        float v0[7], v1[7], v2[7];
+#pragma unroll
+        for (int it = 0; it < 7; ++it) {
+            v0[it] = sg[(2 * it) * kGlSeg + 4 * kHop];
+            v1[it] = sg[(2 * it + 1) * kGlSeg + 2 * kHop];
+            v2[it] = sg[(2 * it + 2) * kGlSeg];
+        }
+        const float nrm_steady = __ldg(tb.inv_wss + (r % kHop));
+#pragma unroll
+        for (int it = 0; it < 7; ++it) {
+            const int l = 320 + tid + kFeThreads * it;              // local padded offset in the tile
             const int p = span0 + l;                                // padded position
             const int s = p - kNfft / 2;                            // whole-signal sample index
             if (s < out_first || s >= out_end || s >= Lw) continue;
-            int u_lo = l >= kGlSeg ? (l - kGlSeg) / (2 * kHop) + 1 : 0;
-            int u_hi = l / (2 * kHop);
-            if (u_hi > kFeUnits - 1) u_hi = kFeUnits - 1;
             float acc = 0.f;
-            for (int uu = u_lo; uu <= u_hi; ++uu) acc += seg[uu * kGlSeg + (l - uu * 2 * kHop)];
-            const float nrm = steady ? __ldg(tb.inv_wss + (l % kHop)) : inv_wss_at(p, T, tb);
+            acc += v0[it];
+            acc += v1[it];
+            acc += v2[it];
+            const float nrm = steady ? nrm_steady : inv_wss_at(p, T, tb);
             dst[s - out_first] = acc * nrm;
         }
     }
