@@ -199,7 +199,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    cpu_bind = None
     if world > 1:
+        # one process per GPU: keep the rank (and the pinned buffers it is about to allocate) on the GPU's NUMA node
+        from speech_cloner_b200 import distributed as D
+        cpu_bind = D.bind_to_gpu_cpus(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -481,7 +485,8 @@ def main():
                                    "(sr 16000, n_fft 400, hop 80, 80 mels, 40 MFCC + delta)",
                        "frames_per_step_per_gpu": frames, "fft_precision": args.precision,
                        "l2": "inputs+outputs (361.6 MB) larger than L2, no flush",
-                       "parallelism": f"utterance shards, {world} rank(s), no data-path collective"},
+                       "parallelism": f"utterance shards, {world} rank(s), no data-path collective",
+                       "cpu_binding_rank0": (f"{len(cpu_bind)} cores local to the GPU (NVML)" if cpu_bind else "none")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "frontend_fp32_mode": alt, "griffin_lim": gl, "sweep_10h": sweep,
         }

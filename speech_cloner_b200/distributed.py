@@ -18,6 +18,8 @@ tests (world_size 2) with an oracle-based step function.
 """
 from __future__ import annotations
 
+import os
+
 from typing import Callable, List, Optional, Sequence
 
 import numpy as np
@@ -27,6 +29,31 @@ HALO_FRAMES = 6
 
 
 # --------------------------------------------------------------------------- sharding
+def bind_to_gpu_cpus(device_index: int) -> Optional[List[int]]:
+    """Pin this process to the CPU cores NVML reports as local to GPU ``device_index`` (same NUMA node / PCIe root).
+
+    One process per GPU moves its features through pinned host buffers; Linux places those pages on the NUMA node of
+    the allocating thread, so a rank that runs on the far socket sends every download across the inter-socket link and
+    the host-buffer (`e2e`) rate of an 8-GPU node collapses.  Call this before allocating pinned memory
+    (``FrontendPipeline``).  Returns the cores now allowed, or ``None`` when NVML has nothing to say (single node,
+    restricted container): the affinity is then left alone.
+    """
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        local = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1}
+        allowed = sorted(local & set(os.sched_getaffinity(0)))
+        if not allowed or len(allowed) == len(os.sched_getaffinity(0)):
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
+
+
 def shard_by_frames(lengths: Sequence[int], world_size: int, hop_length: int = 80) -> List[List[int]]:
     """Longest-processing-time greedy partition of utterance indices, balanced by frame count.
 
