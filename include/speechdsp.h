@@ -8,6 +8,15 @@
  * negative sc_status; sc_last_error() gives the message.  No exceptions cross the ABI and
  * there is NO CPU fallback: without a CUDA device every compute entry point fails.
  *
+ * Threading / streams: a plan owns per-call state (descriptor staging, workspaces), so it is
+ * SINGLE-THREADED - a second thread entering a call on the same plan gets SC_ERR_INVALID; create
+ * one plan per thread.  Calls on one plan are ordered: when the stream changes between calls the
+ * library makes the new stream wait for the work queued on the old one.  A plan belongs to the
+ * device that was current in sc_plan_create; calling it with another device current is
+ * SC_ERR_INVALID.  After sc_plan_reserve() compute calls within the reserved bounds do not
+ * allocate (sc_alloc_count() counts the library's allocations; tests assert it stays put).
+ * The only extension of sc_params over the reference's keyword arguments is fft_precision.
+ *
  * Ragged batches: utterance u owns samples [sample_offsets[u], sample_offsets[u+1]) of the
  * packed waveform buffer and frames [frame_offsets[u], frame_offsets[u+1]) of the packed,
  * TIME-MAJOR feature buffers (row = frame, as audio_lib.py:207-211 returns them).  Gaps
@@ -64,6 +73,20 @@ typedef struct sc_params {
 int sc_plan_create(const sc_params* params, sc_plan** plan_out);
 void sc_plan_destroy(sc_plan* plan);
 
+/* Pre-size every buffer of the plan (workspaces, descriptor staging, pinned host slots) for batches of
+ * up to max_utts utterances / spectrograms holding max_samples samples and max_frames frames in total.
+ * Calls within these bounds then never call cudaMalloc / cudaFree / cudaMallocHost; larger calls still
+ * work (they grow the buffers, which synchronises the device).  SURVEY.md section 8(b), last row. */
+int sc_plan_reserve(sc_plan* plan, int64_t max_samples, int64_t max_frames, int32_t max_utts);
+
+/* cudaMalloc + cudaMallocHost calls made by the library so far (all plans). */
+int64_t sc_alloc_count(void);
+
+/* Device-side error flags raised by kernels of this plan since the last poll; waits for `stream`.
+ * bit 0: sc_frontend_batch met an utterance whose mean|y| is 0 or whose gain is not finite
+ *        (audio_lib.py:126 divides by zero there and librosa.stft then raises "not finite everywhere"). */
+int sc_plan_poll_status(sc_plan* plan, int32_t* flags_out, void* stream);
+
 /* 1 if (n_fft, hop_length) take the hand-tuned FFT-400 kernels, 0 for the generic-size kernels. */
 int sc_plan_is_fast_path(const sc_plan* plan);
 
@@ -107,6 +130,9 @@ int sc_phn_target_batch(sc_plan* plan, const int32_t* phn_start_dev, const int32
  * (scipy.signal.lfilter promotes), zero initial state, one signal of n samples. */
 int sc_preemphasis(const float* wav_dev, int64_t n, double coeff, double* out_dev, void* stream);
 int sc_inv_preemphasis(const float* wav_dev, int64_t n, double coeff, double* out_dev, void* stream);
+/* the same for float64 input (lfilter keeps float64 input in float64) */
+int sc_preemphasis_f64(const double* wav_dev, int64_t n, double coeff, double* out_dev, void* stream);
+int sc_inv_preemphasis_f64(const double* wav_dev, int64_t n, double coeff, double* out_dev, void* stream);
 
 /* Prologue of from_power_to_wav (audio_lib.py:290-298): P = max(0, P); optional `realse`
  * power law with mean preservation; A = sqrt(10^(0.1 * (P / p_db_norm_factor - 80))).
@@ -155,11 +181,60 @@ int sc_griffinlim_chunk_step(sc_plan* plan, const float* amp_dev, const float* p
                              int64_t wav_first, int64_t wav_count, float* wav_out_dev, int64_t out_first,
                              int64_t out_count, void* stream);
 
+/* ---- time-chunked long-form path (BASELINE.json configs[3]) ------------------
+ * One rank owns the samples [own_first, own_first + own_count) of a signal of n_frames_total frames
+ * (hop * (n_frames_total - 1) samples).  sc_chunk_geometry gives the constants a caller cuts with:
+ *   align_frames       cut points must be multiples of this many hops (tile grid of the iteration
+ *                      kernel and 256-sample grid of the de-emphasis scan)
+ *   halo_samples/_frames  reach of ONE iteration on each side (samples of waveform, rows of magnitude)
+ *   sum_block_samples  block size of the canonical |y| / power sums (= hop * align_frames)
+ * Everything below is computed on the whole-signal grid, so the assembled result is bit-identical
+ * to the single-GPU one for any number of ranks. */
+int sc_chunk_geometry(const sc_plan* plan, int64_t* align_frames, int64_t* halo_samples, int64_t* halo_frames,
+                      int64_t* sum_block_samples);
+
+/* n_steps Griffin-Lim iterations (audio_lib.py:259-270) on this rank's chunk, queued back to back on
+ * `stream`.  wav_a_dev / wav_b_dev both cover samples [ext_first, ext_first + ext_count), the chunk
+ * plus n_steps * halo_per_step samples each side (less at the signal ends); amp_dev (and phase0_dev)
+ * hold rows first_frame .. first_frame + n_frames_local.  Step m reads a (m even) or b (m odd) and
+ * writes the other over the chunk widened by (n_steps - 1 - m) * halo_per_step: the caller exchanges
+ * halos once per call instead of once per iteration (communication-avoiding form of the per-iteration
+ * exchange in SURVEY.md section 8(e)).  phase0_dev != NULL makes step 0 the initial inverse STFT (:256-260),
+ * which does not read a waveform.  The result is in b when n_steps is odd, in a when it is even. */
+int sc_griffinlim_chunk_run(sc_plan* plan, const float* amp_dev, const float* phase0_dev, int64_t first_frame,
+                            int64_t n_frames_local, int64_t n_frames_total, float* wav_a_dev, float* wav_b_dev,
+                            int64_t ext_first, int64_t ext_count, int64_t own_first, int64_t own_count,
+                            int32_t n_steps, int64_t halo_per_step, void* stream);
+
+/* Prologue (audio_lib.py:290-298) on a chunk.  With realse != 1 the two means of :293/:296 span the whole
+ * signal: sc_p2a_chunk_partial writes 2 float64 per block of align_frames rows (sum P, sum P^realse) of
+ * this rank's rows, the caller all_gathers them in rank order and passes all n_blocks_total pairs on. */
+int sc_p2a_chunk_partial(sc_plan* plan, const float* p_dev, int64_t n_rows, double realse, double* partial_out_dev,
+                         void* stream);
+int sc_p2a_chunk_apply(sc_plan* plan, const float* p_dev, int64_t n_rows, double p_db_norm_factor, double realse,
+                       const double* all_partials_dev, int64_t n_blocks_total, float* amp_dev, void* stream);
+
+/* Epilogue (audio_lib.py:301-306) on a chunk [first, first + count) of a signal of `total` samples.
+ *   sc_deemph_chunk_window  entries of loc a rank needs from its left neighbour (0: coefficient too close
+ *                           to 1 for the windowed carry - de-emphasise on one GPU)
+ *   sc_deemph_chunk_local   loc_out_dev[k] = zero-state response at the end of 256-sample chunk k
+ *   sc_deemph_chunk_apply   loc_ext_dev = n_halo entries from the left neighbour (its last ones; zeros
+ *                           for the first rank) followed by this rank's loc; writes float64 samples and
+ *                           one float64 sum of |y| per block of sum_block_samples
+ *   sc_renorm_chunk         y *= target / (sum of ALL ranks' block sums in order / total) */
+int sc_deemph_chunk_window(double coeff);
+int sc_deemph_chunk_local(sc_plan* plan, const float* wav_dev, int64_t first, int64_t count, int64_t total,
+                          double coeff, double* loc_out_dev, void* stream);
+int sc_deemph_chunk_apply(sc_plan* plan, const float* wav_dev, int64_t first, int64_t count, int64_t total,
+                          double coeff, const double* loc_ext_dev, int32_t n_halo, double* out_dev,
+                          double* block_sums_dev, void* stream);
+int sc_renorm_chunk(sc_plan* plan, double* out_dev, int64_t count, const double* all_block_sums_dev,
+                    int64_t n_blocks_total, int64_t total, double mean_abs_amp_norm, void* stream);
+
 /* Per-kernel device timing for the roofline report (bench.py).  When enabled, the next
  * sc_frontend_batch / sc_griffinlim_batch records CUDA events between its kernels on the caller's
  * stream; sc_profile_read waits for them and returns milliseconds:
- *   after sc_frontend_batch:   ms[0] gain (|y| mean), ms[1] pass A (STFT..mel), ms[2] pass B (summed over the
- *                              L2-resident utterance groups), ms[3] = number of groups
+ *   after sc_frontend_batch:   ms[0] gain (|y| mean), ms[1] pass A (STFT..mel), ms[2] pass B, ms[3] = 1
  *   after sc_griffinlim_batch: ms[0] initial inverse STFT, ms[1] the n_iters-1 iterations, ms[2] 0, ms[3] = n_iters */
 int sc_profile_enable(sc_plan* plan, int32_t on);
 int sc_profile_read(sc_plan* plan, double* ms_out4);

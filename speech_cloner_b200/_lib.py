@@ -44,6 +44,9 @@ _I64P = C.POINTER(C.c_int64)
 PROTOTYPES = {
     "sc_plan_create": (C.c_int, [C.POINTER(ScParams), C.POINTER(_P)]),
     "sc_plan_destroy": (None, [_P]),
+    "sc_plan_reserve": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32]),
+    "sc_alloc_count": (C.c_int64, []),
+    "sc_plan_poll_status": (C.c_int, [_P, C.POINTER(C.c_int32), _P]),
     "sc_plan_is_fast_path": (C.c_int, [_P]),
     "sc_num_frames": (C.c_int64, [_P, C.c_int64]),
     "sc_frontend_batch": (C.c_int, [_P, _P, _I64P, _I64P, C.c_int32, _P, _P, _P, _I64P, _P]),
@@ -51,12 +54,23 @@ PROTOTYPES = {
     "sc_phn_target_batch": (C.c_int, [_P, _P, _P, _I64P, _I64P, C.c_int32, C.c_int32, C.c_int32, _P, _I64P, _P]),
     "sc_preemphasis": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P]),
     "sc_inv_preemphasis": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P]),
+    "sc_preemphasis_f64": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P]),
+    "sc_inv_preemphasis_f64": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P]),
     "sc_power_to_amp_batch": (C.c_int, [_P, _P, _I64P, _I64P, C.c_int32, C.c_double, C.c_double, _P, _P]),
     "sc_griffinlim_batch": (C.c_int, [_P, _P, _P, _I64P, _I64P, C.c_int32, C.c_int32, _P, _I64P, _P, _P]),
     "sc_deemph_renorm_batch": (C.c_int, [_P, _P, _I64P, _I64P, C.c_int32, C.c_double, C.c_double, _P, _P]),
     "sc_transpose_to_f32": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
     "sc_griffinlim_chunk_step": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64,
                                            C.c_int64, _P, C.c_int64, C.c_int64, _P]),
+    "sc_chunk_geometry": (C.c_int, [_P, _I64P, _I64P, _I64P, _I64P]),
+    "sc_griffinlim_chunk_run": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P, C.c_int64, C.c_int64,
+                                          C.c_int64, C.c_int64, C.c_int32, C.c_int64, _P]),
+    "sc_p2a_chunk_partial": (C.c_int, [_P, _P, C.c_int64, C.c_double, _P, _P]),
+    "sc_p2a_chunk_apply": (C.c_int, [_P, _P, C.c_int64, C.c_double, C.c_double, _P, C.c_int64, _P, _P]),
+    "sc_deemph_chunk_window": (C.c_int, [C.c_double]),
+    "sc_deemph_chunk_local": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_double, _P, _P]),
+    "sc_deemph_chunk_apply": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_double, _P, C.c_int32, _P, _P, _P]),
+    "sc_renorm_chunk": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_double, _P]),
     "sc_profile_enable": (C.c_int, [_P, C.c_int32]),
     "sc_profile_read": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "sc_launch_count": (C.c_int64, []),

@@ -107,7 +107,9 @@ class DspPlan:
         win = kw.get("window", "hann")
         wkey = win if isinstance(win, (str, tuple, float, int)) else ("arr", np.asarray(win).tobytes())
         torch = _require_cuda()
-        key = (torch.cuda.current_device(), wkey) + tuple(sorted((k, v) for k, v in kw.items() if k != "window"))
+        # a plan is single-threaded (speechdsp.h): one cached plan per (device, thread, parameter set)
+        key = (torch.cuda.current_device(), threading.get_ident(), wkey) + \
+            tuple(sorted((k, v) for k, v in kw.items() if k != "window"))
         with cls._lock:
             plan = cls._cache.get(key)
             if plan is None:
@@ -116,6 +118,16 @@ class DspPlan:
 
     def num_frames(self, n_samples: int) -> int:
         return 1 + int(n_samples) // self.hop_length
+
+    def reserve(self, max_samples: int, max_frames: int, max_utts: int) -> None:
+        """Pre-size every buffer of the plan so that later calls within these bounds never allocate (``sc_plan_reserve``)."""
+        _lib.check(self._lib.sc_plan_reserve(self._h, int(max_samples), int(max_frames), int(max_utts)), "sc_plan_reserve")
+
+    def poll_status(self) -> int:
+        """Device-side error flags since the last poll (waits for the current stream); bit 0 = all-zero utterance."""
+        flags = C.c_int32(0)
+        _lib.check(self._lib.sc_plan_poll_status(self._h, C.byref(flags), _stream_ptr(_torch())), "sc_plan_poll_status")
+        return int(flags.value)
 
     def profile(self, on: bool) -> None:
         """Record CUDA events between the kernels of the next batch call (see ``sc_profile_enable``)."""
@@ -155,6 +167,12 @@ def _valid_audio(y):
         raise ValueError("Audio buffer is not finite everywhere")
 
 
+def _valid_gain(y, mean_abs_amp_norm):
+    """All-zero audio: the reference's gain (audio_lib.py:126) divides by zero and librosa.stft then raises."""
+    if mean_abs_amp_norm != 1.0 and not y.any():
+        raise ValueError("Audio buffer is not finite everywhere (all-zero audio has no finite gain)")
+
+
 def _is_tensor(x) -> bool:
     return type(x).__module__.startswith("torch")
 
@@ -168,6 +186,15 @@ def _to_dev_f32(x, torch):
 
 def _align(n: int, a: int) -> int:
     return (n + a - 1) // a * a
+
+
+def _to_host(torch, *tensors):
+    """Device tensors -> NumPy arrays through pinned memory (one asynchronous copy each, one synchronisation)."""
+    outs = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors]
+    for o, t in zip(outs, tensors):
+        o.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return tuple(o.numpy() for o in outs)
 
 
 # ---------------------------------------------------------------------------- front-end
@@ -252,6 +279,7 @@ def calc_MFCC_input_batch(wavs, sr=16000, pre_emphasis=0.97, hop_length=40, win_
     if not device_in:
         for w in wavs:
             _valid_audio(w)                                   # before any device work, like librosa.stft
+            _valid_gain(w, mean_abs_amp_norm)
     torch = _require_cuda()
     plan = _plan_from_kwargs(sr, pre_emphasis, hop_length, win_length, n_mels, n_mfcc, n_fft, window,
                              mfcc_normaleze_first_mfcc, mfcc_norm_factor, calc_mfcc_derivate, M_dB_norm_factor,
@@ -262,14 +290,17 @@ def calc_MFCC_input_batch(wavs, sr=16000, pre_emphasis=0.97, hop_length=40, win_
         for w, o in zip(wavs, layout.sample_offsets):
             wav_dev[o:o + w.shape[0]] = w
     else:
-        host = torch.zeros(layout.total_samples, dtype=torch.float32).pin_memory()
+        host = torch.empty(layout.total_samples, dtype=torch.float32, pin_memory=True)   # torch's caching pinned allocator
         hv = host.numpy()
-        for w, o in zip(wavs, layout.sample_offsets):
+        for w, o, o1 in zip(wavs, layout.sample_offsets, layout.sample_offsets[1:]):
             hv[o:o + w.shape[0]] = w
+            hv[o + w.shape[0]:o1] = 0.0
         wav_dev = host.to("cuda", non_blocking=True)
     mfcc, mel, pdb = frontend_device(plan, wav_dev, layout)
+    if device_in and plan.poll_status() & 1:
+        raise ValueError("Audio buffer is not finite everywhere (all-zero audio has no finite gain)")
     if not (return_device or device_in):
-        mfcc, mel, pdb = mfcc.cpu().numpy(), mel.cpu().numpy(), pdb.cpu().numpy()
+        mfcc, mel, pdb = _to_host(torch, mfcc, mel, pdb)
     out = []
     for o, t in zip(layout.frame_offsets, layout.frames):
         out.append((mfcc[o:o + t], mel[o:o + t], pdb[o:o + t]))
@@ -316,11 +347,16 @@ def _emphasis(wav, coeff, inverse: bool):
         wav = np.asarray(wav)
         if wav.ndim != 1:
             raise ValueError("wav must be one-dimensional")
-    x = _to_dev_f32(wav, torch)
+    # scipy.signal.lfilter computes in float64 whatever the input: float64 input is NOT rounded to float32 first
+    f64 = (wav.dtype == torch.float64) if device_in else (wav.dtype == np.float64)
+    if f64:
+        x = wav.to(device="cuda").contiguous() if device_in else torch.from_numpy(np.ascontiguousarray(wav)).cuda()
+        fn, name = (lib.sc_inv_preemphasis_f64, "sc_inv_preemphasis_f64") if inverse else (lib.sc_preemphasis_f64, "sc_preemphasis_f64")
+    else:
+        x = _to_dev_f32(wav, torch)
+        fn, name = (lib.sc_inv_preemphasis, "sc_inv_preemphasis") if inverse else (lib.sc_preemphasis, "sc_preemphasis")
     out = torch.empty(x.shape[0], dtype=torch.float64, device="cuda")
-    fn = lib.sc_inv_preemphasis if inverse else lib.sc_preemphasis
-    _lib.check(fn(x.data_ptr(), x.shape[0], float(coeff), out.data_ptr(), _stream_ptr(torch)),
-               "sc_inv_preemphasis" if inverse else "sc_preemphasis")
+    _lib.check(fn(x.data_ptr(), x.shape[0], float(coeff), out.data_ptr(), _stream_ptr(torch)), name)
     return out if device_in else out.cpu().numpy()
 
 
@@ -476,6 +512,8 @@ def _print_rms(rms_row):
 
 def griffin_lim_alg(stft_amp, win_length, hop_length, num_iters=300, n_fft=None, verbose=True, phase0=None):
     """Griffin-Lim from a (1+n_fft//2, T) magnitude; returns float32 (hop*(T-1),) (audio_lib.py:249-274)."""
+    if int(num_iters) < 1:
+        return None                                                   # the reference's loop never runs: `wav = None` (:252)
     torch = _require_cuda()
     lib = _lib.load()
     plan = _gl_plan(win_length, hop_length, n_fft)
@@ -514,13 +552,58 @@ def griffin_lim_batch(amps, win_length, hop_length, num_iters=300, n_fft=None, p
     return outs if return_device else [w.cpu().numpy() for w in outs]
 
 
+def _stage_rows(items, layout, n_bins, torch, transpose_from_freq_major: bool, lib):
+    """List of per-utterance arrays / tensors -> one packed time-major float32 CUDA buffer [rows][n_bins].
+
+    Host arrays travel in ONE pinned staging buffer and one asynchronous copy (the per-utterance ``.cuda()`` calls of
+    round 1 cost more than the Griffin-Lim prologue they fed).  ``transpose_from_freq_major``: the items are
+    (n_bins, T) in the reference's orientation (float32 or float64) and are transposed on the device.
+    """
+    rows = layout.frame_offsets[-1]
+    dst = torch.zeros((rows, n_bins), dtype=torch.float32, device="cuda")
+    st = _stream_ptr(torch)
+    if all(_is_tensor(x) for x in items):
+        for x, o, t in zip(items, layout.frame_offsets, layout.frames):
+            if transpose_from_freq_major:
+                dst[o:o + t] = x.to(device="cuda", dtype=torch.float32).t()
+            else:
+                dst[o:o + t] = x.to(device="cuda", dtype=torch.float32)
+        return dst
+    arrs = [x.cpu().numpy() if _is_tensor(x) else np.asarray(x) for x in items]
+    if not transpose_from_freq_major:
+        host = torch.empty((rows, n_bins), dtype=torch.float32, pin_memory=True)
+        hv = host.numpy()
+        for a, o, o1, t in zip(arrs, layout.frame_offsets, layout.frame_offsets[1:], layout.frames):
+            hv[o:o + t] = a
+            hv[o + t:o1] = 0.0
+        dst.copy_(host, non_blocking=True)
+        return dst
+    f64 = any(a.dtype == np.float64 for a in arrs)
+    dt_np, dt_t = (np.float64, torch.float64) if f64 else (np.float32, torch.float32)
+    offs = [0]
+    for t in layout.frames:
+        offs.append(offs[-1] + t * n_bins)
+    host = torch.empty(offs[-1], dtype=dt_t, pin_memory=True)
+    hv = host.numpy()
+    for a, o, t in zip(arrs, offs, layout.frames):
+        hv[o:o + t * n_bins] = np.ascontiguousarray(a, dtype=dt_np).reshape(-1)
+    src = host.to("cuda", non_blocking=True)
+    for o, fo, t in zip(offs, layout.frame_offsets, layout.frames):
+        _lib.check(lib.sc_transpose_to_f32(src.data_ptr() + o * src.element_size(), int(f64), n_bins, t,
+                                           dst.data_ptr() + fo * n_bins * 4, st), "sc_transpose_to_f32")
+    return dst
+
+
 def from_power_to_wav_batch(Ps, P_dB_norm_factor=0.01, pre_emphasis=0.97, hop_length=40, win_length=800,
                             mean_abs_amp_norm=0.01, n_iter=200, n_fft=None, realse=1.0, verbose=False,
                             phase0s=None, return_device=False):
     """``from_power_to_wav`` over a list of (T, bins) spectrograms as one ragged GPU batch.
 
-    ``phase0s`` is a list of (bins, T) initial phases (reference orientation) or ``None``.
+    ``phase0s`` is a list of (bins, T) initial phases (reference orientation) or ``None`` (drawn per utterance from the
+    global NumPy state in list order, like calling the reference in a loop).
     """
+    if int(n_iter) < 1:
+        raise ValueError("n_iter must be >= 1 (the reference's griffin_lim_alg returns None for 0 iterations)")
     torch = _require_cuda()
     lib = _lib.load()
     plan = _gl_plan(win_length, hop_length, n_fft)
@@ -532,27 +615,26 @@ def from_power_to_wav_batch(Ps, P_dB_norm_factor=0.01, pre_emphasis=0.97, hop_le
             raise ValueError("P needs at least 2 frames")
     layout = _GlLayout([P.shape[0] for P in Ps], plan.hop_length)
     n = len(Ps)
-    p_dev = torch.zeros((layout.frame_offsets[-1], plan.n_bins), dtype=torch.float32, device="cuda")
-    ph_dev = torch.zeros_like(p_dev)
-    for i, (P, o) in enumerate(zip(Ps, layout.frame_offsets)):
-        p_dev[o:o + P.shape[0]] = _to_dev_f32(P, torch)
-        ph = phase0s[i] if phase0s is not None else np.pi * np.random.rand(plan.n_bins, P.shape[0])
-        ph_dev[o:o + P.shape[0]] = _freq_major_to_dev(ph, plan.n_bins, torch, lib)
+    if phase0s is None:
+        phase0s = [np.pi * np.random.rand(plan.n_bins, P.shape[0]) for P in Ps]      # :255
+    p_dev = _stage_rows(Ps, layout, plan.n_bins, torch, False, lib)
+    ph_dev = _stage_rows(list(phase0s), layout, plan.n_bins, torch, True, lib)
     st = _stream_ptr(torch)
-    amp_dev = torch.empty_like(p_dev)
     _lib.check(lib.sc_power_to_amp_batch(plan._h, p_dev.data_ptr(), layout.c_frame_offsets, layout.c_frame_counts,
-                                         n, float(P_dB_norm_factor), float(realse), amp_dev.data_ptr(), st),
-               "sc_power_to_amp_batch")
+                                         n, float(P_dB_norm_factor), float(realse), p_dev.data_ptr(), st),
+               "sc_power_to_amp_batch")                                              # in place (the header allows aliasing)
     rms = torch.zeros((n, int(n_iter)), dtype=torch.float32, device="cuda") if verbose else None
-    wav = griffin_lim_device(plan, amp_dev, ph_dev, layout, int(n_iter), rms)
+    wav = griffin_lim_device(plan, p_dev, ph_dev, layout, int(n_iter), rms)
     if verbose:
         _print_rms(rms[0].cpu().numpy())
     out = torch.empty(layout.sample_offsets[-1], dtype=torch.float64, device="cuda")
     _lib.check(lib.sc_deemph_renorm_batch(plan._h, wav.data_ptr(), layout.c_sample_offsets, layout.c_sample_lengths,
                                           n, float(pre_emphasis), float(mean_abs_amp_norm), out.data_ptr(), st),
                "sc_deemph_renorm_batch")
-    outs = [out[o:o + m] for o, m in zip(layout.sample_offsets, layout.samples)]
-    return outs if return_device else [w.cpu().numpy() for w in outs]
+    if return_device:
+        return [out[o:o + m] for o, m in zip(layout.sample_offsets, layout.samples)]
+    host, = _to_host(torch, out)
+    return [host[o:o + m] for o, m in zip(layout.sample_offsets, layout.samples)]
 
 
 def from_power_to_wav(P,

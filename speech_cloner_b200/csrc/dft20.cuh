@@ -94,95 +94,12 @@ SC_HD void dft20_scalar(cx<R> (&v)[20]) {
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Packed float32 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2: one instruction works on a register PAIR).
-// A complex float lives in one 64-bit register (x low, y high); ptxas folds half swaps and scalar broadcasts into
-// operand modifiers (R.F32x2.LO_HI, R.F32), so "multiply by +-i" and "times a real constant" cost nothing extra.
-// Every packed operation below performs exactly the two scalar operations of the scalar code (same operands, same
-// order, one rounding each), so results are bit-identical to the scalar butterflies.
-#ifdef __CUDA_ARCH__
-struct f2 { unsigned long long v; };
-__device__ __forceinline__ f2 pk(float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void unpk(f2 p, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v)); }
-__device__ __forceinline__ f2 swp(f2 p) { float a, b; unpk(p, a, b); return pk(b, a); }
-__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
-__device__ __forceinline__ f2 bc(float c) { return pk(c, c); }
-
-// (a.x + b.y, a.y - b.x) = a - i*b   and   (a.x - b.y, a.y + b.x) = a + i*b, as one FFMA2 each on the swapped b
-__device__ __forceinline__ f2 add_mi(f2 a, f2 b) { return fma2(swp(b), pk(1.0f, -1.0f), a); }
-__device__ __forceinline__ f2 add_pi(f2 a, f2 b) { return fma2(swp(b), pk(-1.0f, 1.0f), a); }
-
-template <bool INV>
-__device__ __forceinline__ void radix4_pk(f2& a0, f2& a1, f2& a2, f2& a3) {
-    const f2 s0 = add2(a0, a2), d0 = sub2(a0, a2);
-    const f2 s1 = add2(a1, a3), d1 = sub2(a1, a3);
-    a0 = add2(s0, s1);
-    a2 = sub2(s0, s1);
-    const f2 p = add_mi(d0, d1);       // d0 - i*d1
-    const f2 m = add_pi(d0, d1);       // d0 + i*d1
-    a1 = INV ? m : p;
-    a3 = INV ? p : m;
-}
-
-template <bool INV>
-__device__ __forceinline__ void radix5_pk(f2& a0, f2& a1, f2& a2, f2& a3, f2& a4) {
-    constexpr float C1 = 0.30901699437494742410f, C2 = -0.80901699437494742410f;
-    constexpr float S1 = 0.95105651629515357212f, S2 = 0.58778525229247312917f;
-    const f2 t1 = add2(a1, a4), t3 = sub2(a1, a4);
-    const f2 t2 = add2(a2, a3), t4 = sub2(a2, a3);
-    const f2 m1 = fma2(bc(C2), t2, fma2(bc(C1), t1, a0));
-    const f2 m2 = fma2(bc(C1), t2, fma2(bc(C2), t1, a0));
-    const f2 q1 = fma2(bc(S2), t4, mul2(bc(S1), t3));
-    const f2 q2 = fma2(bc(-S1), t4, mul2(bc(S2), t3));
-    a0 = add2(add2(a0, t1), t2);
-    const f2 x1 = add_mi(m1, q1), x4 = add_pi(m1, q1);
-    const f2 x2 = add_mi(m2, q2), x3 = add_pi(m2, q2);
-    a1 = INV ? x4 : x1;
-    a4 = INV ? x1 : x4;
-    a2 = INV ? x3 : x2;
-    a3 = INV ? x2 : x3;
-}
-
-template <bool INV>
-__device__ __forceinline__ void dft20_pk(cx<float> (&v)[20]) {
-    f2 t[4][5];
-#pragma unroll
-    for (int n2 = 0; n2 < 5; ++n2) {
-        f2 a0 = pk(v[(0 + 4 * n2) % 20].x, v[(0 + 4 * n2) % 20].y), a1 = pk(v[(5 + 4 * n2) % 20].x, v[(5 + 4 * n2) % 20].y);
-        f2 a2 = pk(v[(10 + 4 * n2) % 20].x, v[(10 + 4 * n2) % 20].y), a3 = pk(v[(15 + 4 * n2) % 20].x, v[(15 + 4 * n2) % 20].y);
-        radix4_pk<INV>(a0, a1, a2, a3);
-        t[0][n2] = a0; t[1][n2] = a1; t[2][n2] = a2; t[3][n2] = a3;
-    }
-#pragma unroll
-    for (int k1 = 0; k1 < 4; ++k1) {
-        radix5_pk<INV>(t[k1][0], t[k1][1], t[k1][2], t[k1][3], t[k1][4]);
-#pragma unroll
-        for (int k2 = 0; k2 < 5; ++k2) unpk(t[k1][k2], v[(5 * k1 + 16 * k2) % 20].x, v[(5 * k1 + 16 * k2) % 20].y);
-    }
-}
-#endif  // __CUDA_ARCH__
-
-// dispatch: float32 on the device takes the packed butterflies, everything else (float64, host) the scalar ones
 template <bool INV, typename R>
 SC_HD void dft20(cx<R> (&v)[20]) {
     dft20_scalar<INV>(v);
 }
-// Measured on B200 (Griffin-Lim, 64 x 1000 frames): the packed form halves the butterfly instructions but FFMA2 holds
-// the FP32 pipe for two cycles and the 64-bit register pairs raise pressure under the 96-register cap (104 bytes of
-// spills): 0.0758 -> 0.0816 ms per iteration.  Kept as an opt-in (-DSC_USE_F32X2) for kernels with register headroom.
-#ifdef SC_USE_F32X2
-template <bool INV>
-SC_HD void dft20(cx<float> (&v)[20]) {
-#ifdef __CUDA_ARCH__
-    dft20_pk<INV>(v);
-#else
-    dft20_scalar<INV>(v);
-#endif
-}
-#endif
+// (A packed FADD2 / FFMA2 form of these butterflies was measured in round 1 and was slower under Griffin-Lim's
+// 96-register cap: 0.0758 -> 0.0816 ms per iteration; it is not part of the product.)
 
 // ---------------------------------------------------------------------------------------------------
 // Real-input 20-point DFT (forward) and its Hermitian-input inverse, same Good-Thomas 4 x 5 graph with

@@ -45,15 +45,14 @@ struct FeParams {
 //   n <= 128 : 8 strided accumulators r[j] += a[i+j], res = ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)),
 //              then the n % 8 tail added one by one          (n < 8: plain left-to-right sum)
 //   n >  128 : n2 = n/2 rounded down to a multiple of 8;  sum(a[:n2]) + sum(a[n2:])
-// The tree depends only on n.  Each CTA owns the subtree `idx` at depth D (D chosen on the host so
-// that a subtree has <= kAbsSubtree samples), expands it into a 255-node heap in shared memory,
-// reduces the leaves with 8-lane groups and folds the heap bottom-up; k_gain_finalize folds the top
-// D levels.  Verified bitwise against numpy in tests/test_gpu_frontend.py::test_gain_matches_numpy.
+// The tree depends only on n.  Each CTA owns subtrees `idx` at depth D (D chosen on the host so
+// that a subtree has <= kAbsSubtree samples) and writes their sums into a per-utterance heap; the top D levels
+// are folded by k_gain_finalize.  Verified bitwise against numpy through the kernel the hot path launches
+// (tests/test_gpu_frontend.py::test_gain_matches_numpy_bitwise).
 #ifndef SC_ABS_SUBTREE
 #define SC_ABS_SUBTREE 8000
 #endif
 constexpr int kAbsSubtree = SC_ABS_SUBTREE;
-constexpr int kAbsThreads = 256;
 
 __host__ __device__ inline int abs_depth(int64_t n) {
     int d = 0;
@@ -61,263 +60,18 @@ __host__ __device__ inline int abs_depth(int64_t n) {
     return d;
 }
 
-__global__ void __launch_bounds__(kAbsThreads) k_abs_pairwise(const float* __restrict__ wav, Ragged rg,
-                                                              const int64_t* __restrict__ heap_off,
-                                                              float* __restrict__ heap) {
-    __shared__ int hs[256];
-    __shared__ int hn[256];
-    __shared__ float hv[256];
-    const int tid = threadIdx.x;
-    const int u = find_utt(rg.tile_prefix, rg.n_utts, blockIdx.x);
-    const int idx = blockIdx.x - rg.tile_prefix[u];
-    const int64_t len = rg.sample_len[u];
-    const int D = abs_depth(len);
-    int64_t start = 0, n = len;
-    for (int b = D - 1; b >= 0; --b) {
-        int64_t n2 = n / 2;
-        n2 -= n2 % 8;
-        if ((idx >> b) & 1) { start += n2; n -= n2; } else { n = n2; }
-    }
-    const float* __restrict__ a = wav + rg.sample_off[u] + start;
-    if (tid == 0) { hs[1] = 0; hn[1] = (int)n; }
-    __syncthreads();
-    for (int l = 0; l < 7; ++l) {
-        if (tid < (1 << l)) {
-            const int i = (1 << l) + tid;
-            const int m = hn[i];
-            if (m > 128) {
-                int n2 = m / 2;
-                n2 -= n2 % 8;
-                hs[2 * i] = hs[i]; hn[2 * i] = n2;
-                hs[2 * i + 1] = hs[i] + n2; hn[2 * i + 1] = m - n2;
-            } else {
-                hn[2 * i] = 0; hn[2 * i + 1] = 0;
-            }
-        }
-        __syncthreads();
-    }
-    // leaves: one 8-lane group per node
-    {
-        const int g = tid >> 3, j = tid & 7;
-        const unsigned gmask = 0xffu << (8 * ((tid & 31) >> 3));     // the 8 lanes of this group only
-        for (int i = 1 + g; i < 256; i += kAbsThreads / 8) {
-            const int m = hn[i];
-            if (m <= 0 || m > 128) continue;
-            const float* __restrict__ p = a + hs[i];
-            float res;
-            if (m < 8) {
-                res = 0.f;
-                for (int k = 0; k < m; ++k) res += fabsf(__ldg(p + k));
-            } else {
-                const int body = m - (m % 8);
-                float v[16];                              // a leaf has <= 128 samples: <= 16 per lane, all loaded first
-#pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = 8 * q < body ? __ldg(p + 8 * q + j) : 0.f;
-                float r = fabsf(v[0]);
-#pragma unroll
-                for (int q = 1; q < 16; ++q)
-                    if (8 * q < body) r += fabsf(v[q]);
-                r += __shfl_xor_sync(gmask, r, 1, 8);
-                r += __shfl_xor_sync(gmask, r, 2, 8);
-                r += __shfl_xor_sync(gmask, r, 4, 8);
-                res = r;
-                for (int k = body; k < m; ++k) res += fabsf(__ldg(p + k));
-            }
-            if (j == 0) hv[i] = res;
-        }
-    }
-    __syncthreads();
-    for (int l = 6; l >= 0; --l) {
-        if (tid < (1 << l)) {
-            const int i = (1 << l) + tid;
-            if (hn[i] > 128) hv[i] = hv[2 * i] + hv[2 * i + 1];
-        }
-        __syncthreads();
-    }
-    if (tid == 0) heap[heap_off[u] + (1 << D) + idx] = hv[1];
-}
-
-// Second form of the leaf pass: no shared-memory heap and one barrier.  Every 8-lane group derives the bounds of
-// "its" depth-7 slot arithmetically (the tree depends only on n), sums the leaf exactly like NumPy's unrolled
-// block, and writes one of 128 slot values; a node that is already a leaf above depth 7 is owned by its first
-// slot and the other slots hold +0, so folding the 128 slots as a perfect binary tree reproduces NumPy's order
-// (x + 0 = x exactly for the non-negative sums).  (u, subtree index) of a CTA come from a host-built table.
-constexpr int kAbs2Threads = 512;
-__global__ void __launch_bounds__(kAbs2Threads) k_abs_pairwise2(const float* __restrict__ wav, Ragged rg,
-                                                                const int2* __restrict__ recs,
-                                                                const int64_t* __restrict__ heap_off,
-                                                                float* __restrict__ heap) {
-    __shared__ __align__(16) float hv[128];
-    const int tid = threadIdx.x;
-    const int2 rec = __ldg(recs + blockIdx.x);
-    const int u = rec.x, idx = rec.y;
-    const int64_t len = rg.sample_len[u];
-    const int D = abs_depth(len);
-    int64_t start = 0, n64 = len;
-    for (int b = D - 1; b >= 0; --b) {
-        int64_t n2 = n64 / 2;
-        n2 -= n2 % 8;
-        if ((idx >> b) & 1) { start += n2; n64 -= n2; } else { n64 = n2; }
-    }
-    const float* __restrict__ a = wav + rg.sample_off[u] + start;
-    const int n = (int)n64;
-    const int g = tid >> 3, j = tid & 7;
-    constexpr int kRounds = 128 / (kAbs2Threads / 8);
-    int ls[kRounds], ln[kRounds];
-    bool own[kRounds];
-#pragma unroll
-    for (int r = 0; r < kRounds; ++r) {
-        const int s = g + (kAbs2Threads / 8) * r;
-        int o = 0, m = n;
-        bool first = true;
-#pragma unroll
-        for (int lvl = 6; lvl >= 0; --lvl) {
-            const int bit = (s >> lvl) & 1;
-            if (m > 128) {
-                int n2 = m / 2;
-                n2 -= n2 % 8;
-                if (bit) { o += n2; m -= n2; } else { m = n2; }
-            } else if (bit) {
-                first = false;
-            }
-        }
-        ls[r] = o; ln[r] = m; own[r] = first && m > 0;
-    }
-    // all loads of both rounds first
-    float v[kRounds][16], tl[kRounds][7];
-#pragma unroll
-    for (int r = 0; r < kRounds; ++r) {
-        const float* __restrict__ p = a + ls[r];
-        const int m = own[r] ? ln[r] : 0;
-        const int body = m >= 8 ? m - (m % 8) : 0;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) v[r][q] = 8 * q < body ? __ldg(p + 8 * q + j) : 0.f;
-#pragma unroll
-        for (int q = 0; q < 7; ++q) tl[r][q] = body + q < m ? __ldg(p + body + q) : 0.f;
-    }
-#pragma unroll
-    for (int r = 0; r < kRounds; ++r) {
-        const int m = own[r] ? ln[r] : 0;
-        const int body = m >= 8 ? m - (m % 8) : 0;
-        float acc = fabsf(v[r][0]);
-#pragma unroll
-        for (int q = 1; q < 16; ++q)
-            if (8 * q < body) acc += fabsf(v[r][q]);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-        float res = body > 0 ? acc : 0.f;                  // m < 8: plain left-to-right sum of the tail
-#pragma unroll
-        for (int q = 0; q < 7; ++q)
-            if (body + q < m) res += fabsf(tl[r][q]);
-        if (j == 0) hv[g + (kAbs2Threads / 8) * r] = res;
-    }
-    __syncthreads();
-    if (tid < 32) {
-        const float4 x = reinterpret_cast<const float4*>(hv)[tid];
-        float t = (x.x + x.y) + (x.z + x.w);
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (tid == 0) heap[heap_off[u] + (1 << D) + idx] = t;
-    }
-}
-
-// Third form of the leaf pass: the CTA stages its subtree (<= kAbsSubtree samples) in shared memory with coalesced
+// The leaf pass: the CTA stages its subtree (<= kAbsSubtree samples) in shared memory with coalesced
 // 128-bit loads, then ONE THREAD per depth-7 slot sums its leaf with NumPy's 8 accumulators held in registers
-// (two float4 per step: no shuffles, 1.25 instructions per sample).  The staged copy is padded by 4 words per 128
-// samples so that leaves that start 128 samples apart fall into different bank groups.
+// (two float4 per step: no shuffles, 1.25 instructions per sample).  Every thread derives the bounds of "its"
+// depth-7 slot arithmetically (the tree depends only on n); a node that is already a leaf above depth 7 is owned by
+// its first slot and the other slots hold +0, so folding the 128 slots as a perfect binary tree reproduces NumPy's
+// order (x + 0 = x exactly for the non-negative sums).  The staged copy is padded by 4 words per 128 samples so
+// that leaves that start 128 samples apart fall into different bank groups.
 constexpr int kAbs3Threads = 128;
 constexpr int kAbs3Smem = kAbsSubtree + 4 * (kAbsSubtree / 128 + 1);
 __device__ __forceinline__ int abs3_pos(int i) { return i + ((i >> 7) << 2); }
-__global__ void __launch_bounds__(kAbs3Threads) k_abs_pairwise3(const float* __restrict__ wav, Ragged rg,
-                                                                const int2* __restrict__ recs,
-                                                                const int64_t* __restrict__ heap_off,
-                                                                float* __restrict__ heap) {
-    __shared__ __align__(16) float buf[kAbs3Smem];
-    __shared__ __align__(16) float hv[128];
-    const int tid = threadIdx.x;
-    const int2 rec = __ldg(recs + blockIdx.x);
-    const int u = rec.x, idx = rec.y;
-    const int64_t len = rg.sample_len[u];
-    const int D = abs_depth(len);
-    int64_t start = 0, n64 = len;
-    for (int b = D - 1; b >= 0; --b) {
-        int64_t n2 = n64 / 2;
-        n2 -= n2 % 8;
-        if ((idx >> b) & 1) { start += n2; n64 -= n2; } else { n64 = n2; }
-    }
-    const float* __restrict__ a = wav + rg.sample_off[u] + start;
-    const int n = (int)n64;
-    // ---- stage: all loads first (<= 16 float4 per thread), then the padded stores
-    if ((reinterpret_cast<uintptr_t>(a) & 15) == 0) {
-        constexpr int kIt = (kAbsSubtree / 4 + kAbs3Threads - 1) / kAbs3Threads;
-        const float4* __restrict__ a4 = reinterpret_cast<const float4*>(a);
-        const int n4 = n >> 2;
-        float4 v[kIt];
-#pragma unroll
-        for (int it = 0; it < kIt; ++it) {
-            const int e = tid + it * kAbs3Threads;
-            if (e < n4) v[it] = __ldg(a4 + e);
-        }
-#pragma unroll
-        for (int it = 0; it < kIt; ++it) {
-            const int e = tid + it * kAbs3Threads;
-            if (e < n4) *reinterpret_cast<float4*>(buf + abs3_pos(4 * e)) = v[it];
-        }
-        for (int e = (n4 << 2) + tid; e < n; e += kAbs3Threads) buf[abs3_pos(e)] = __ldg(a + e);
-    } else {
-        for (int e = tid; e < n; e += kAbs3Threads) buf[abs3_pos(e)] = __ldg(a + e);
-    }
-    // ---- bounds of this thread's depth-7 slot (see k_abs_pairwise2)
-    int o = 0, m = n;
-    bool first = true;
-#pragma unroll
-    for (int lvl = 6; lvl >= 0; --lvl) {
-        const int bit = (tid >> lvl) & 1;
-        if (m > 128) {
-            int n2 = m / 2;
-            n2 -= n2 % 8;
-            if (bit) { o += n2; m -= n2; } else { m = n2; }
-        } else if (bit) {
-            first = false;
-        }
-    }
-    __syncthreads();
-    float res = 0.f;
-    if (first && m > 0) {
-        // o is a multiple of 8 and a leaf never crosses more than one 128-sample pad boundary unaligned:
-        // pad boundaries are multiples of 128, float4 groups start at multiples of 4
-        if (m < 8) {
-            for (int k = 0; k < m; ++k) res += fabsf(buf[abs3_pos(o + k)]);
-        } else {
-            const int body = m - (m % 8);
-            float4 lo = *reinterpret_cast<const float4*>(buf + abs3_pos(o));
-            float4 hi = *reinterpret_cast<const float4*>(buf + abs3_pos(o + 4));
-            float r0 = fabsf(lo.x), r1 = fabsf(lo.y), r2 = fabsf(lo.z), r3 = fabsf(lo.w);
-            float r4 = fabsf(hi.x), r5 = fabsf(hi.y), r6 = fabsf(hi.z), r7 = fabsf(hi.w);
-#pragma unroll 4
-            for (int i = 8; i < body; i += 8) {
-                lo = *reinterpret_cast<const float4*>(buf + abs3_pos(o + i));
-                hi = *reinterpret_cast<const float4*>(buf + abs3_pos(o + i + 4));
-                r0 += fabsf(lo.x); r1 += fabsf(lo.y); r2 += fabsf(lo.z); r3 += fabsf(lo.w);
-                r4 += fabsf(hi.x); r5 += fabsf(hi.y); r6 += fabsf(hi.z); r7 += fabsf(hi.w);
-            }
-            res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
-            for (int k = body; k < m; ++k) res += fabsf(buf[abs3_pos(o + k)]);
-        }
-    }
-    hv[tid] = res;
-    __syncthreads();
-    if (tid < 32) {
-        const float4 x = reinterpret_cast<const float4*>(hv)[tid];
-        float t = (x.x + x.y) + (x.z + x.w);
-#pragma unroll
-        for (int s = 1; s < 32; s <<= 1) t += __shfl_xor_sync(0xffffffffu, t, s);
-        if (tid == 0) heap[heap_off[u] + (1 << D) + idx] = t;
-    }
-}
 
-// Fourth form: abs3's arithmetic in a persistent CTA.  Sub-tree records (source offset, length, heap slot) come
+// Persistent CTAs.  Sub-tree records (source offset, length, heap slot) come
 // from k_fe_setup; the loads of sub-tree i+1 and the record of sub-tree i+2 are in flight while sub-tree i is
 // summed, so the kernel streams the audio instead of paying the record -> data latency chain once per CTA.
 struct AbsRec {
@@ -419,7 +173,7 @@ __global__ void __launch_bounds__(kAbs3Threads, 4) k_abs_pairwise4(const float* 
 __global__ void __launch_bounds__(128) k_gain_finalize(Ragged rg, const int64_t* __restrict__ heap_off,
                                                        float* __restrict__ heap, UttStat* __restrict__ stat,
                                                        double mean_abs_amp_norm, int use_gain,
-                                                       float* __restrict__ mean_out) {
+                                                       float* __restrict__ mean_out, int32_t* __restrict__ status) {
     const int u = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (u >= rg.n_utts) return;
     const int lane = threadIdx.x & 31;
@@ -437,6 +191,9 @@ __global__ void __launch_bounds__(128) k_gain_finalize(Ragged rg, const int64_t*
         const float mean32 = __fdiv_rn(h[1], (float)len);
         gain = (float)(mean_abs_amp_norm / (double)mean32);
         if (mean_out && lane == 0) mean_out[u] = mean32;
+        // all-zero (or non-finite) audio: numpy divides by zero here and librosa.stft then raises;
+        // the host polls this flag (sc_plan_poll_status)
+        if (status && lane == 0 && !(mean32 > 0.0f && isfinite(gain))) atomicOr(status, 1);
     }
     if (lane == 0) {
         UttStat st;
@@ -655,189 +412,6 @@ k_fe_pass_a(const float* __restrict__ wav, Ragged rg, FeTables tb, FeParams prm,
     fe_epilogue_a<THREADS>(sm.power, F, kBins, nfr, sm.mel_w, sm.mel_istart, tb, mel_db, sm.red,
                            stat + u, pdb_out + (rg.frame_off[u] + t0) * kBins,
                            mel_raw + (rg.frame_off[u] + t0) * n_mels);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Persistent, warp-specialised pass A (all tiles of utterances at least two tiles long).
-//   warps 0 .. UNITS*20/32-1 : UNITS units x 20 threads compute tile i
-//   last warp (producer)      : finds tile i+1, writes its descriptor and streams its raw samples
-//                               into the other half of a double buffer with cp.async (LDGSTS)
-// One full-CTA barrier per tile hands a buffer over; the compute warps synchronise among
-// themselves with a named barrier, so the producer's global-load latency never stalls them.
-// Gain and pre-emphasis are applied on the fly when a unit picks its 24 strided samples.
-struct TileDescA {
-    int64_t frame_row;      // first output row of the tile
-    int64_t q0;             // utterance sample index of the tile's first (reflect-padded) sample
-    int64_t L;              // utterance length
-    int32_t u, t0, valid;
-    int32_t edge;           // the tile touches the reflect padding (first / last tiles of an utterance)
-    int32_t nfr;            // frames of the tile that exist
-    float gain;
-};
-
-template <typename R, int UNITS>
-struct FeSmemP {
-    static constexpr int F = 2 * UNITS;
-    static constexpr int SPAN = kHop * (F - 1) + kNfft;
-    static constexpr int RAW = SPAN + 8;                 // raw[i + 4] = y[reflect(q0 + i)]; 16-byte aligned start, +1 look-ahead
-    static constexpr int CTHREADS = UNITS * kUnitThreads;
-    R win[kNfft];
-    cx<R> slots[UNITS * kUnitSlots];
-    cx<R> w400[sizeof(R) == 8 ? kNfft : 1];
-    alignas(16) float raw[3][RAW];                       // 3-slot ring of cp.async 16-byte destinations
-    float power[F * kBins];
-    float2 mel_w[kBins];
-    int32_t mel_istart[kMaxMels + 2];
-    float red[4][(CTHREADS + 31) / 32];
-    TileDescA desc[3];
-    // followed by mel_db[F][n_mels + 1]
-};
-
-template <typename R, int UNITS>
-__global__ void __launch_bounds__(UNITS * kUnitThreads + 32, sizeof(R) == 8 ? 2 : 3)
-k_fe_pass_a_persist(const float* __restrict__ wav, Ragged rg, int total_tiles, FeTables tb, FeParams prm,
-                    UttStat* __restrict__ stat, float* __restrict__ pdb_out, float* __restrict__ mel_raw) {
-    using SM = FeSmemP<R, UNITS>;
-    constexpr int F = SM::F, RAW = SM::RAW, CT = SM::CTHREADS, ALL = CT + 32;
-    static_assert(CT % 32 == 0, "compute threads must fill whole warps");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SM& sm = *reinterpret_cast<SM*>(smem_raw);
-    float* mel_db = reinterpret_cast<float*>(smem_raw + sizeof(SM));
-    constexpr bool kF64 = sizeof(R) == 8;
-    const int tid = threadIdx.x;
-    const int n_mels = tb.n_mels;
-
-    if (tid >= CT) {
-        // ================================ producer warp ================================
-        const int lane = tid - CT;
-        // issue(): descriptor + asynchronous copy of one tile's raw samples into ring slot b (one commit group)
-        auto issue = [&](int tile, int b) -> int {
-            TileDescA d;
-            d.valid = tile < total_tiles;
-            d.u = 0; d.t0 = 0; d.gain = 0.f; d.frame_row = 0; d.q0 = 0; d.L = 1; d.edge = 0; d.nfr = 0;
-            if (d.valid) {
-                const int u = find_utt(rg.tile_prefix, rg.n_utts, tile);
-                const int k = rg.int_first[u] + (tile - rg.tile_prefix[u]);
-                d.u = u; d.t0 = k * F;
-                d.nfr = min(F, rg.frame_cnt[u] - d.t0);
-                d.gain = stat[u].gain;
-                d.frame_row = rg.frame_off[u] + d.t0;
-                d.L = rg.sample_len[u];
-                d.q0 = (int64_t)d.t0 * kHop - kNfft / 2;
-                d.edge = !(d.q0 - 4 >= 0 && d.q0 + SM::SPAN + 4 <= d.L);
-                const float* __restrict__ y = wav + rg.sample_off[u];
-                float* dst = sm.raw[b];
-                if (!d.edge) {
-                    const float* __restrict__ src = y + (d.q0 - 4);
-                    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-                        for (int i = lane; i < RAW / 4; i += 32) cp_async16(dst + 4 * i, src + 4 * i);
-                    } else {
-                        for (int i = lane; i < RAW; i += 32) cp_async4(dst + i, src + i);
-                    }
-                } else {
-                    // first / last tiles: np.pad(.., 'reflect') (:147) as a gather; the host guarantees a single
-                    // reflection per side (utterances shorter than 2 tiles go to the plain kernel)
-                    for (int i = lane; i < RAW; i += 32) {
-                        const int64_t q = d.q0 - 4 + i;
-                        const int64_t r = q < 0 ? -q : (q > d.L - 1 ? 2 * (d.L - 1) - q : q);
-                        cp_async4(dst + i, y + r);
-                    }
-                }
-            }
-            cp_async_commit();
-            if (lane == 0) sm.desc[b] = d;
-            return d.valid;
-        };
-        // two tiles in flight: while the compute warps work on tile i, tile i+1 has landed (or is
-        // landing) and tile i+2 is being requested, so one tile period hides the whole
-        // search -> descriptor -> DRAM latency chain
-        const int G = gridDim.x;
-        int tile = blockIdx.x;
-        int ok_cur = issue(tile, 0);
-        int ok_next = issue(tile + G, 1);
-        cp_async_wait_group<1>();
-        bar_sync<0, ALL>();                       // B_0: tile 0 ready
-        int i = 0;
-        while (ok_cur) {
-            const int ok_n2 = issue(tile + 2 * G, (i + 2) % 3);
-            cp_async_wait_group<1>();             // tile i+1 landed
-            bar_sync<0, ALL>();                   // B_{i+1}
-            ok_cur = ok_next; ok_next = ok_n2;
-            tile += G; ++i;
-        }
-        return;
-    }
-
-    // ================================== compute warps ==================================
-    if (kF64) {
-        for (int i = tid; i < kNfft; i += CT) {
-            sm.win[i] = (R)(2.0 * tb.win_half_d[i]);
-            sm.w400[i] = mk<R>((R)tb.w400_d[i].x, (R)tb.w400_d[i].y);
-        }
-    } else {
-        for (int i = tid; i < kNfft; i += CT) sm.win[i] = (R)(2.0f * tb.win_half[i]);
-    }
-    for (int i = tid; i < kBins; i += CT) sm.mel_w[i] = tb.mel_w[i];
-    for (int i = tid; i < n_mels + 2; i += CT) sm.mel_istart[i] = tb.mel_istart[i];
-    const int unit = tid / kUnitThreads;
-    const int j = tid - unit * kUnitThreads;
-    typename FeTw<R>::type tw;
-    if (kF64) tw.load(reinterpret_cast<const cx<R>*>(sm.w400), j);
-    else tw.load(reinterpret_cast<const cx<R>*>(tb.w400), j);
-    cx<R>* unit_slots = sm.slots + unit * kUnitSlots;
-    const double c = prm.pre_emphasis;
-    int b = 0;
-    bar_sync<0, ALL>();
-    while (true) {
-        const TileDescA d = sm.desc[b];
-        if (!d.valid) break;
-        // ---- step 1 with gain (float32) + pre-emphasis (float64) applied on the fly
-        {
-            const float* __restrict__ src = sm.raw[b] + 4 + unit * (2 * kHop) + j;
-            R s[24];
-            if (!d.edge) {
-#pragma unroll
-                for (int m = 0; m < 24; ++m) {
-                    const float cur = d.gain * src[20 * m];
-                    const float prev = d.gain * src[20 * m - 1];
-                    s[m] = (R)((double)cur - c * (double)prev);
-                }
-            } else {
-                // y[r - 1] of a reflected sample is its right-hand neighbour in the padded order; y[-1] = 0 (:27)
-                const int64_t qb = d.q0 + unit * (2 * kHop) + j;
-#pragma unroll
-                for (int m = 0; m < 24; ++m) {
-                    const int64_t q = qb + 20 * m;
-                    const float cur = d.gain * src[20 * m];
-                    const float nb = (q < 0 || q > d.L - 1) ? src[20 * m + 1] : src[20 * m - 1];
-                    const float prev = q == 0 ? 0.0f : d.gain * nb;
-                    s[m] = (R)((double)cur - c * (double)prev);
-                }
-            }
-            R xa[20], xb[20];
-#pragma unroll
-            for (int n1 = 0; n1 < 20; ++n1) {
-                const R w = sm.win[20 * n1 + j];
-                xa[n1] = s[n1] * w;
-                xb[n1] = s[n1 + 4] * w;
-            }
-            fwd_step1_real(xa, xb, tw, unit_slots + j);
-        }
-        bar_sync<1, CT>();
-        {
-            int u2, c2;
-            step2_task<true>(tid, UNITS, u2, c2);
-            cx<R> v[20];
-            fwd_step2(v, sm.slots + u2 * kUnitSlots + c2 * kSlotLd);
-            float* pa = sm.power + (2 * u2) * kBins;
-            store_power(v, c2, pa, pa + kBins);
-        }
-        bar_sync<1, CT>();
-        fe_epilogue_a<CT, 1>(sm.power, F, kBins, d.nfr, sm.mel_w, sm.mel_istart, tb, mel_db, sm.red, stat + d.u,
-                             pdb_out + d.frame_row * kBins, mel_raw + d.frame_row * n_mels);
-        bar_sync<0, ALL>();
-        b = b == 2 ? 0 : b + 1;
-    }
 }
 
 // ---------------------------------------------------------------------------------------------

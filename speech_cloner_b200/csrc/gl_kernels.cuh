@@ -435,27 +435,31 @@ __global__ void __launch_bounds__(128) k_rms_delta_final(const GlJob* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// from_power_to_wav prologue (:290-298)
+// from_power_to_wav prologue (:290-298).
+// The two means of the `realse` power law (:293, :296) are summed in a CANONICAL order that does not depend on how a
+// long spectrogram is cut into per-rank chunks: one float64 partial per block of `block_rows` frames on the
+// whole-signal grid (fixed thread / warp order inside a block), and a sequential sum over the blocks in order.
+// A time-chunked run (ranks all_gather their block partials) therefore gets bit-identical scale factors.
 struct P2aJob {
-    int64_t row0;       // first row
-    int64_t rows;       // frames
-    int32_t tile0;
-    int32_t pad;
+    int64_t row0;       // first row of this job in the p / amp buffers
+    int64_t rows;       // frames present
+    int32_t tile0;      // prefix of apply tiles (kP2aChunk elements each)
+    int32_t blk0;       // prefix of sum blocks
 };
-constexpr int kP2aChunk = 16384;   // elements per tile
+constexpr int kP2aChunk = 16384;   // elements per apply tile
 
-// partial sums of max(0,P) and max(0,P)^realse  (:293, :296)
+// partial sums of max(0,P) and max(0,P)^realse over one block of `block_rows` frames
 __global__ void __launch_bounds__(256) k_p2a_partial(const float* __restrict__ p, const P2aJob* __restrict__ jobs,
-                                                    int n_jobs, const int32_t* __restrict__ prefix, int bins,
-                                                    float realse, double* __restrict__ partial) {
-    const int ji = find_utt(prefix, n_jobs, blockIdx.x);
+                                                    int n_jobs, const int32_t* __restrict__ blk_prefix, int bins,
+                                                    int block_rows, float realse, double* __restrict__ partial) {
+    const int ji = find_utt(blk_prefix, n_jobs, blockIdx.x);
     const P2aJob job = jobs[ji];
-    const int64_t n = job.rows * bins;
-    const int64_t begin = (int64_t)(blockIdx.x - prefix[ji]) * kP2aChunk;
-    const int64_t end = begin + kP2aChunk < n ? begin + kP2aChunk : n;
-    const float* __restrict__ src = p + job.row0 * bins;
+    const int64_t r0 = (int64_t)(blockIdx.x - blk_prefix[ji]) * block_rows;
+    const int64_t r1 = r0 + block_rows < job.rows ? r0 + block_rows : job.rows;
+    const float* __restrict__ src = p + (job.row0 + r0) * bins;
+    const int64_t n = (r1 - r0) * bins;
     double s0 = 0.0, s1 = 0.0;
-    for (int64_t i = begin + threadIdx.x; i < end; i += 256) {
+    for (int64_t i = threadIdx.x; i < n; i += 256) {
         const float v = fmaxf(src[i], 0.0f);
         s0 += (double)v;
         s1 += (double)powf(v, realse);
@@ -472,30 +476,29 @@ __global__ void __launch_bounds__(256) k_p2a_partial(const float* __restrict__ p
     }
 }
 
-__global__ void __launch_bounds__(128) k_p2a_scale(const P2aJob* __restrict__ jobs, int n_jobs,
-                                                  const int32_t* __restrict__ prefix,
+// (p_mean / P.mean()) in float32 (:296; the element counts cancel): sequential sum of the block partials.
+// `partial` holds blk_prefix[n_jobs] pairs; job j owns pairs [blk_prefix[j], blk_prefix[j+1]).
+__global__ void __launch_bounds__(128) k_p2a_scale(int n_jobs, const int32_t* __restrict__ blk_prefix,
                                                   const double* __restrict__ partial, float* __restrict__ scale) {
-    const int ji = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int ji = blockIdx.x * 128 + threadIdx.x;
     if (ji >= n_jobs) return;
-    const int lane = threadIdx.x & 31;
     double s0 = 0.0, s1 = 0.0;
-    for (int t = prefix[ji] + lane; t < prefix[ji + 1]; t += 32) { s0 += partial[2 * t]; s1 += partial[2 * t + 1]; }
-    s0 = warp_sum(s0); s1 = warp_sum(s1);
-    // (p_mean / P.mean()) in float32 (:296); the element counts cancel
-    if (lane == 0) scale[ji] = (float)s0 / (float)s1;
+    for (int t = blk_prefix[ji]; t < blk_prefix[ji + 1]; ++t) { s0 += partial[2 * t]; s1 += partial[2 * t + 1]; }
+    scale[ji] = (float)s0 / (float)s1;
 }
 
-__global__ void __launch_bounds__(256) k_p2a_apply(const float* __restrict__ p, const P2aJob* __restrict__ jobs,
+// p and amp may be the same buffer (element-wise, in place): no __restrict__ on them
+__global__ void __launch_bounds__(256) k_p2a_apply(const float* p, const P2aJob* __restrict__ jobs,
                                                   int n_jobs, const int32_t* __restrict__ prefix, int bins,
                                                   float realse, int use_realse, const float* __restrict__ scale,
-                                                  float inv_norm, float* __restrict__ amp) {
+                                                  float inv_norm, float* amp) {
     const int ji = find_utt(prefix, n_jobs, blockIdx.x);
     const P2aJob job = jobs[ji];
     const int64_t n = job.rows * bins;
     const int64_t begin = (int64_t)(blockIdx.x - prefix[ji]) * kP2aChunk;
     const int64_t end = begin + kP2aChunk < n ? begin + kP2aChunk : n;
-    const float* __restrict__ src = p + job.row0 * bins;
-    float* __restrict__ dst = amp + job.row0 * bins;
+    const float* src = p + job.row0 * bins;
+    float* dst = amp + job.row0 * bins;
     const float sc = use_realse ? scale[ji] : 1.0f;
     for (int64_t i = begin + threadIdx.x; i < end; i += 256) {
         float v = fmaxf(src[i], 0.0f);
@@ -506,37 +509,55 @@ __global__ void __launch_bounds__(256) k_p2a_apply(const float* __restrict__ p, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// from_power_to_wav epilogue (:301-306): de-emphasis IIR in float64 as a three-phase chunked scan,
+// from_power_to_wav epilogue (:301-306): de-emphasis IIR y[n] = x[n] + c*y[n-1] in float64 as a chunked scan,
 // then y * (m / mean|y|).
+//
+// A signal is cut into chunks of kIirChunk samples on its own grid (sample 0 starts a chunk).  Phase 1 computes the
+// zero-state response at the end of every chunk (`loc`).  The state entering chunk k is
+//     S_k = loc[k-1] + c^256 * loc[k-2] + c^512 * loc[k-3] + ...
+// and c^256 is tiny for the reference's coefficients (0.97^256 = 4e-4), so the series is cut after `win` terms
+// chosen on the host such that |c|^(256*win) < 1e-40 (12 terms for 0.97): phase 2 evaluates it per chunk with a
+// Horner chain over the previous `win` entries of `loc` - no sequential pass over the signal, and a time-chunked run
+// only needs the last `win` values of its left neighbour (one small message per boundary).  Every
+// quantity is computed on the whole-signal grid, so chunked and unchunked runs are bit-identical.  Coefficients too
+// close to 1 for a short window (win > kIirMaxWin) take the sequential carry kernel instead (single GPU only).
+// mean|y| uses a canonical order as well: float64 partial per chunk (sequential in the owning thread), sequential sum of
+// the `blk_chunks` chunk partials of a block, sequential sum of the blocks.
 constexpr int kIirChunk = 256;       // samples per thread-sequential chunk
-constexpr int kIirBlock = 128;       // chunks per block
+constexpr int kIirBlock = 128;       // chunks per CTA
+constexpr int kIirMaxWin = 64;
 
 struct WavJob {
-    int64_t off;      // element offset
-    int64_t len;      // samples
-    int32_t tile0;    // prefix of blocks (kIirChunk * kIirBlock samples each)
-    int32_t chunk0;   // prefix of chunks
+    int64_t off;      // element offset of the first sample of this job in the wav / out buffers
+    int64_t len;      // samples present in this job
+    int64_t first;    // whole-signal index of that sample (multiple of kIirChunk); 0 for a whole signal
+    int64_t total;    // whole-signal length (renormalisation divides by it)
+    int32_t tile0;    // prefix of CTAs (kIirBlock chunks each)
+    int32_t chunk0;   // prefix of entries in the `loc` array: this job owns [chunk0, chunk0 + halo + n_chunks)
+    int32_t blk0;     // prefix of |y| sum blocks
+    int32_t halo;     // entries of `loc` in front of chunk 0 (zeros, or the left neighbour's last chunks)
 };
 
 // phase 1: zero-state response at the end of each chunk
-__global__ void __launch_bounds__(kIirBlock) k_iir_local(const float* __restrict__ x, const WavJob* __restrict__ jobs,
+template <typename TIN>
+__global__ void __launch_bounds__(kIirBlock) k_iir_local(const TIN* __restrict__ x, const WavJob* __restrict__ jobs,
                                                         int n_jobs, const int32_t* __restrict__ prefix, double c,
-                                                        double* __restrict__ chunk_end) {
+                                                        double* __restrict__ loc) {
     const int ji = find_utt(prefix, n_jobs, blockIdx.x);
     const WavJob job = jobs[ji];
     const int chunk = (blockIdx.x - prefix[ji]) * kIirBlock + threadIdx.x;
     const int64_t begin = (int64_t)chunk * kIirChunk;
     if (begin >= job.len) return;
     const int64_t end = begin + kIirChunk < job.len ? begin + kIirChunk : job.len;
-    const float* __restrict__ src = x + job.off;
+    const TIN* __restrict__ src = x + job.off;
     double y = 0.0;
     for (int64_t i = begin; i < end; ++i) y = (double)src[i] + c * y;
-    chunk_end[job.chunk0 + chunk] = y;
+    loc[job.chunk0 + job.halo + chunk] = y;
 }
 
-// phase 2: carry into each chunk, sequential over the chunks of one signal (one thread per job)
+// fallback phase 2 (|c| close to 1): sequential carry over the chunks of one signal, `loc` becomes the incoming states
 __global__ void __launch_bounds__(32) k_iir_carry(const WavJob* __restrict__ jobs, int n_jobs, double c,
-                                                 double* __restrict__ chunk_end) {
+                                                 double* __restrict__ loc) {
     const int ji = blockIdx.x * 32 + threadIdx.x;
     if (ji >= n_jobs) return;
     const WavJob job = jobs[ji];
@@ -544,64 +565,85 @@ __global__ void __launch_bounds__(32) k_iir_carry(const WavJob* __restrict__ job
     double cl = 1.0;                                   // c^kIirChunk
     for (int i = 0; i < kIirChunk; ++i) cl *= c;
     double carry = 0.0;                                // state entering chunk k
+    double* __restrict__ l = loc + job.chunk0 + job.halo;
     for (int64_t k = 0; k < n_chunks; ++k) {
-        const double local = chunk_end[job.chunk0 + k];
-        chunk_end[job.chunk0 + k] = carry;             // overwrite with the incoming state
-        const int64_t len = (k + 1) * kIirChunk <= job.len ? kIirChunk : job.len - k * kIirChunk;
-        double cp = cl;
-        if (len != kIirChunk) { cp = 1.0; for (int64_t i = 0; i < len; ++i) cp *= c; }
-        carry = local + cp * carry;
+        const double local = l[k];
+        l[k] = carry;                                  // overwrite with the incoming state
+        carry = local + cl * carry;                    // every chunk but the last is full
     }
 }
 
-// phase 3: rerun each chunk from its incoming state, write float64, accumulate |y| partials
-__global__ void __launch_bounds__(kIirBlock) k_iir_apply(const float* __restrict__ x, const WavJob* __restrict__ jobs,
+// phase 2 + 3: incoming state from the previous `win` chunk responses (win == 0: `loc` already holds the states),
+// rerun the chunk from it, write float64, per-chunk sum of |y|
+template <typename TIN>
+__global__ void __launch_bounds__(kIirBlock) k_iir_apply(const TIN* __restrict__ x, const WavJob* __restrict__ jobs,
                                                         int n_jobs, const int32_t* __restrict__ prefix, double c,
-                                                        const double* __restrict__ chunk_in, double* __restrict__ out,
-                                                        double* __restrict__ abs_partial) {
+                                                        double cl, int win, const double* __restrict__ loc,
+                                                        double* __restrict__ out, double* __restrict__ chunk_abs) {
     const int ji = find_utt(prefix, n_jobs, blockIdx.x);
     const WavJob job = jobs[ji];
     const int chunk = (blockIdx.x - prefix[ji]) * kIirBlock + threadIdx.x;
     const int64_t begin = (int64_t)chunk * kIirChunk;
+    if (begin >= job.len) return;
+    const int64_t end = begin + kIirChunk < job.len ? begin + kIirChunk : job.len;
+    const double* __restrict__ l = loc + job.chunk0 + job.halo + chunk;     // l[-m] = response of chunk - m
+    double y;
+    if (win == 0) {
+        y = l[0];
+    } else {
+        const int reach = chunk + job.halo < win ? chunk + job.halo : win;  // entries that exist in front of this chunk
+        y = 0.0;
+        for (int m = reach; m >= 1; --m) y = l[-m] + cl * y;
+    }
+    const TIN* __restrict__ src = x + job.off;
+    double* __restrict__ dst = out + job.off;
     double a = 0.0;
-    if (begin < job.len) {
-        const int64_t end = begin + kIirChunk < job.len ? begin + kIirChunk : job.len;
-        const float* __restrict__ src = x + job.off;
-        double* __restrict__ dst = out + job.off;
-        double y = chunk_in[job.chunk0 + chunk];
-        for (int64_t i = begin; i < end; ++i) {
-            y = (double)src[i] + c * y;
-            dst[i] = y;
-            a += fabs(y);
-        }
+    for (int64_t i = begin; i < end; ++i) {
+        y = (double)src[i] + c * y;
+        dst[i] = y;
+        a += fabs(y);
     }
-    a = warp_sum(a);
-    __shared__ double red[kIirBlock / 32];
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int w = 0; w < kIirBlock / 32; ++w) t += red[w];
-        abs_partial[blockIdx.x] = t;
-    }
+    chunk_abs[job.chunk0 + job.halo + chunk] = a;
+}
+
+// per-block sums of |y|: block b of a job = its chunks [b * blk_chunks, (b+1) * blk_chunks), summed in order
+__global__ void __launch_bounds__(128) k_abs_blocks(const WavJob* __restrict__ jobs, int n_jobs,
+                                                   const int32_t* __restrict__ blk_prefix, int blk_chunks,
+                                                   const double* __restrict__ chunk_abs, double* __restrict__ blk_sum) {
+    const int b = blockIdx.x * 128 + threadIdx.x;
+    if (b >= blk_prefix[n_jobs]) return;
+    const int ji = find_utt(blk_prefix, n_jobs, b);
+    const WavJob job = jobs[ji];
+    const int64_t n_chunks = (job.len + kIirChunk - 1) / kIirChunk;
+    const int64_t k0 = (int64_t)(b - blk_prefix[ji]) * blk_chunks;
+    const int64_t k1 = k0 + blk_chunks < n_chunks ? k0 + blk_chunks : n_chunks;
+    const double* __restrict__ a = chunk_abs + job.chunk0 + job.halo;
+    double s = 0.0;
+    for (int64_t k = k0; k < k1; ++k) s += a[k];
+    blk_sum[b] = s;
+}
+
+// scale[j] = target / (sum of the job's block sums / total samples); blocks summed in order by one thread.
+// all_blk != nullptr (time-chunked run, one job): sum the n_all block sums of the WHOLE signal instead.
+__global__ void __launch_bounds__(128) k_renorm_scale(const WavJob* __restrict__ jobs, int n_jobs,
+                                                     const int32_t* __restrict__ blk_prefix,
+                                                     const double* __restrict__ blk_sum, const double* __restrict__ all_blk,
+                                                     int n_all, double target, double* __restrict__ scale) {
+    const int ji = blockIdx.x * 128 + threadIdx.x;
+    if (ji >= n_jobs) return;
+    double s = 0.0;
+    if (all_blk) for (int t = 0; t < n_all; ++t) s += all_blk[t];
+    else for (int t = blk_prefix[ji]; t < blk_prefix[ji + 1]; ++t) s += blk_sum[t];
+    scale[ji] = target / (s / (double)jobs[ji].total);
 }
 
 // y *= m / mean|y|   (:306)
 __global__ void __launch_bounds__(256) k_renorm(const WavJob* __restrict__ jobs, int n_jobs,
-                                               const int32_t* __restrict__ prefix,
-                                               const double* __restrict__ abs_partial, double target,
+                                               const int32_t* __restrict__ prefix, const double* __restrict__ scale,
                                                double* __restrict__ out) {
     const int ji = find_utt(prefix, n_jobs, blockIdx.x);
     const WavJob job = jobs[ji];
-    __shared__ double scale_s;
-    if (threadIdx.x < 32) {
-        double s = 0.0;
-        for (int t = prefix[ji] + threadIdx.x; t < prefix[ji + 1]; t += 32) s += abs_partial[t];
-        s = warp_sum(s);
-        if (threadIdx.x == 0) scale_s = target / (s / (double)job.len);
-    }
-    __syncthreads();
-    const double sc = scale_s;
+    const double sc = scale[ji];
     const int64_t begin = (int64_t)(blockIdx.x - prefix[ji]) * (kIirChunk * kIirBlock);
     const int64_t end = begin + kIirChunk * kIirBlock < job.len ? begin + kIirChunk * kIirBlock : job.len;
     double* __restrict__ dst = out + job.off;
@@ -610,7 +652,8 @@ __global__ void __launch_bounds__(256) k_renorm(const WavJob* __restrict__ jobs,
 
 // ---------------------------------------------------------------------------------------------
 // standalone calc_preemphasis (:27): y[n] = x[n] - c*x[n-1], float64 out
-__global__ void __launch_bounds__(256) k_preemph(const float* __restrict__ x, int64_t n, double c,
+template <typename TIN>
+__global__ void __launch_bounds__(256) k_preemph(const TIN* __restrict__ x, int64_t n, double c,
                                                 double* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;

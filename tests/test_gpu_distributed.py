@@ -49,26 +49,34 @@ def _featurize(rank, world):
 
 
 def _chunked(rank, world):
+    """Chunked == unchunked, bit for bit, through the public distributed path (NCCL halo exchange every k iterations,
+    distributed prologue with realse != 1, windowed IIR carry across the boundary, gathered |y| sums)."""
     from oracle import audio_lib_oracle as oracle
+    from speech_cloner_b200 import audio_lib as al
     from speech_cloner_b200 import distributed as D
-    from speech_cloner_b200.audio_lib import DspPlan, _GlLayout, griffin_lim_device
     T = 2001
     base = oracle.calc_MFCC_input(synth.utterance(31, 4.0), **HP)[2]
     P = np.concatenate([base] * 8)[:T]
-    amp = torch.from_numpy(np.sqrt(np.power(np.float32(10.0), np.float32(0.1) * (P / np.float32(0.01) - np.float32(80.0))))
-                           .astype(np.float32)).cuda()
     np.random.seed(4)
-    ph = torch.from_numpy((np.pi * np.random.rand(T, 201)).astype(np.float32)).cuda()
+    ph = np.pi * np.random.rand(201, T)
     n_iter = 25
-    plan = DspPlan.get(n_fft=400, win_length=400, hop_length=80)
-    whole = griffin_lim_device(plan, amp, ph, _GlLayout([T], 80), n_iter)[: 80 * (T - 1)].clone()
-    gl = D.ChunkedGriffinLim(T, 80, 400)
-    f_lo, f_hi = gl.frame_range()
-    chunk = gl.run(amp[f_lo:f_hi].contiguous(), ph[f_lo:f_hi].contiguous(), n_iter)
-    assert torch.equal(chunk, whole[gl.lo:gl.hi])                 # bit-identical to the single-GPU run
-    full = gl.gather(chunk, dst=0)
-    if rank == 0:
-        assert torch.equal(full, whole)
+    for realse, k in ((1.0, 20), (1.2, 4), (1.0, 1)):
+        whole = al.from_power_to_wav(P, P_dB_norm_factor=0.01, pre_emphasis=0.97, hop_length=80, win_length=400,
+                                     mean_abs_amp_norm=0.045, n_iter=n_iter, realse=realse, verbose=False, phase0=ph)
+        gl = D.ChunkedGriffinLim(T, 80, 400, steps_per_exchange=k)
+        assert gl.chunk_geometry_matches_host()
+        f_lo, f_hi = gl.frame_range(n_iters=n_iter)
+        p_loc = torch.from_numpy(np.ascontiguousarray(P[f_lo:f_hi])).cuda()
+        ph_loc = torch.from_numpy(np.ascontiguousarray(ph.T[f_lo:f_hi]).astype(np.float32)).cuda()
+        y = gl.from_power_to_wav(p_loc, ph_loc, P_dB_norm_factor=0.01, pre_emphasis=0.97, mean_abs_amp_norm=0.045,
+                                 n_iter=n_iter, realse=realse)
+        assert y.dtype == torch.float64
+        np.testing.assert_array_equal(y.cpu().numpy(), whole[gl.lo:gl.hi])   # bit-identical to the single-GPU run
+        full = gl.gather(y, dst=0)
+        if rank == 0:
+            np.testing.assert_array_equal(full.cpu().numpy(), whole)
+        else:
+            assert full is None
 
 
 def test_featurize_sharded_nccl():

@@ -126,6 +126,8 @@ def test_fp32_fast_mode_documented_accuracy(al, case):
 
 
 def test_gain_matches_numpy_bitwise(al):
+    """np.abs(y).mean() bit for bit, through the SAME kernels the hot path launches (k_fe_setup -> k_abs_pairwise4 ->
+    k_gain_finalize): sc_mean_abs_batch and sc_frontend_batch share them since round 2."""
     """mean|y| must be NumPy's float32 pairwise sum bit for bit (a 1-ulp gain moves near-floor bins by 3e-5)."""
     import torch
     rng = np.random.default_rng(3)
@@ -227,3 +229,133 @@ def test_host_pipeline_equals_batch_call(al, n_chunks, n_streams, ramp):
     for got, ref in zip(pipe.views(), want):
         for g, r in zip(got, ref):
             np.testing.assert_array_equal(g, r)
+
+
+def test_frontend_gain_is_numpy_exact_inside_the_hot_path(al):
+    """The gain sc_frontend_batch applies is float32(m / float64(np.abs(y).mean())) bit for bit: with every other stage
+    switched to identity-like settings the outputs of two utterances that differ only by an exact power-of-two scale
+    are bit-identical, and a 1-ulp change of one sample's magnitude that flips the float32 mean flips the output."""
+    y = synth.utterance(41, 1.0)
+    a = al.calc_MFCC_input(y, **HP)
+    b = al.calc_MFCC_input((y * np.float32(4.0)).astype(np.float32), **HP)      # mean scales exactly, gain / 4 exactly
+    for p, q in zip(a, b):
+        np.testing.assert_array_equal(p, q)
+
+
+def test_same_layout_reuses_tables_and_results_do_not_change(al):
+    """Second call with the same ragged layout skips the descriptor upload and k_fe_setup (layout cache): one launch
+    fewer, same bits; a different layout in between invalidates it."""
+    import torch
+    lens = [48000, 16001, 7999, 64000]
+    wavs = [synth.utterance(50 + i, n / 16000.0)[:n] for i, n in enumerate(lens)]
+    plan = al.DspPlan(**{**dict(sr=16000, n_fft=400, win_length=400, hop_length=80, n_mels=80, n_mfcc=40),
+                         **{k: HP[k] for k in ("pre_emphasis", "mfcc_norm_factor", "M_dB_norm_factor", "P_dB_norm_factor",
+                                               "mean_abs_amp_norm", "clip_output", "calc_mfcc_derivate",
+                                               "mfcc_normaleze_first_mfcc")}})
+    lay = al.FrontendLayout(lens, 80)
+    dev = torch.zeros(lay.total_samples, dtype=torch.float32, device="cuda")
+    for w, o in zip(wavs, lay.sample_offsets):
+        dev[o:o + len(w)] = torch.from_numpy(w).cuda()
+    al.launch_count_reset()
+    first = [t.clone() for t in al.frontend_device(plan, dev, lay)]
+    n1 = al.launch_count()
+    second = al.frontend_device(plan, dev, lay)
+    n2 = al.launch_count() - n1
+    assert n2 == n1 - 1
+    for p, q in zip(first, second):
+        assert torch.equal(p, q)
+    lay2 = al.FrontendLayout(lens[:2], 80)
+    al.frontend_device(plan, dev, lay2)
+    third = al.frontend_device(plan, dev, lay)
+    for p, q in zip(first, third):
+        assert torch.equal(p, q)
+
+
+def test_no_allocation_after_reserve(al):
+    """SURVEY.md section 8(b), last row: after sc_plan_reserve, compute calls within the bounds never allocate."""
+    import torch
+    from speech_cloner_b200 import _lib
+    lib = _lib.load()
+    lens = [64000] * 6 + [30001, 555]
+    plan = al.DspPlan(sr=16000, n_fft=400, win_length=400, hop_length=80, n_mels=80, n_mfcc=40, calc_mfcc_derivate=True)
+    lay = al.FrontendLayout(lens, 80)
+    plan.reserve(lay.total_samples, lay.total_frames, len(lens))
+    dev = torch.rand(lay.total_samples, dtype=torch.float32, device="cuda") - 0.5
+    out = al.frontend_device(plan, dev, lay)                   # allocates torch outputs only
+    glay = al._GlLayout([t for t in lay.frames], 80)
+    amp = torch.rand((glay.frame_offsets[-1], 201), dtype=torch.float32, device="cuda")
+    ph = torch.rand_like(amp)
+    wav = torch.empty(glay.sample_offsets[-1], dtype=torch.float32, device="cuda")
+    out64 = torch.empty(glay.sample_offsets[-1], dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    torch.cuda.synchronize()
+    n0 = lib.sc_alloc_count()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(2):
+        al.frontend_device(plan, dev, lay, out)
+        _lib.check(lib.sc_power_to_amp_batch(plan._h, amp.data_ptr(), glay.c_frame_offsets, glay.c_frame_counts, len(lens),
+                                             0.01, 1.2, amp.data_ptr(), st), "p2a")
+        al.griffin_lim_device(plan, amp, ph, glay, 3, None, wav)
+        _lib.check(lib.sc_deemph_renorm_batch(plan._h, wav.data_ptr(), glay.c_sample_offsets, glay.c_sample_lengths, len(lens),
+                                              0.97, 0.045, out64.data_ptr(), st), "deemph")
+    torch.cuda.synchronize()
+    assert lib.sc_alloc_count() == n0
+    assert torch.cuda.mem_get_info()[0] == free0                # cudaMemGetInfo delta = 0
+
+
+def test_plan_is_single_threaded_and_ordered_across_streams(al):
+    """A second thread entering a call on the same plan is refused; the public API hands every thread its own plan;
+    a call on another stream is ordered after the previous one."""
+    import threading
+    import torch
+    lens = [64000] * 64
+    plan = al.DspPlan(sr=16000, n_fft=400, win_length=400, hop_length=80, n_mels=80, n_mfcc=40)
+    lay = al.FrontendLayout(lens, 80)
+    dev = torch.rand(lay.total_samples, dtype=torch.float32, device="cuda") - 0.5
+    ref = [t.clone() for t in al.frontend_device(plan, dev, lay)]
+    errors, oks = [], []
+
+    def worker():
+        for _ in range(30):
+            try:
+                al.frontend_device(plan, dev, lay)
+                oks.append(1)
+            except ValueError as e:
+                errors.append(str(e))
+    ths = [threading.Thread(target=worker) for _ in range(4)]
+    [t.start() for t in ths]; [t.join() for t in ths]
+    assert oks and all("single-threaded" in e for e in errors)
+    torch.cuda.synchronize()
+    # other stream: results identical, no explicit synchronisation by the caller
+    s2 = torch.cuda.Stream()
+    out_a = al.frontend_device(plan, dev, lay)
+    with torch.cuda.stream(s2):
+        out_b = al.frontend_device(plan, dev, lay)
+    torch.cuda.synchronize()
+    for p, q, r in zip(ref, out_a, out_b):
+        assert torch.equal(p, q) and torch.equal(p, r)
+    # the reference-signature functions are thread-safe: the plan cache is keyed by thread
+    y = synth.utterance(7, 0.5)
+    want = al.calc_MFCC_input(y, **HP)
+    res = []
+
+    def api_worker():
+        res.append(al.calc_MFCC_input(y, **HP))
+    ths = [threading.Thread(target=api_worker) for _ in range(4)]
+    [t.start() for t in ths]; [t.join() for t in ths]
+    assert len(res) == 4
+    for r in res:
+        for p, q in zip(want, r):
+            np.testing.assert_array_equal(p, q)
+
+
+def test_all_zero_utterance_raises_like_librosa(al):
+    import torch
+    with pytest.raises(ValueError):
+        al.calc_MFCC_input(np.zeros(8000, dtype=np.float32), **HP)
+    with pytest.raises(ValueError):
+        al.calc_MFCC_input(torch.zeros(8000, dtype=torch.float32, device="cuda"), **HP)
+    # the flag is cleared by the poll: the next good call works
+    al.calc_MFCC_input(torch.from_numpy(synth.utterance(3, 0.5)).cuda(), **HP)
+    hp1 = dict(HP); hp1["mean_abs_amp_norm"] = 1.0           # no gain requested: zeros are legal input (:125)
+    al.calc_MFCC_input(np.zeros(8000, dtype=np.float32), **hp1)

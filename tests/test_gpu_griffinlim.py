@@ -152,3 +152,148 @@ def test_chunk_step_equals_unchunked(al):
             torch.cuda.synchronize()
         state, nxt = nxt, state
     np.testing.assert_array_equal(state.cpu().numpy(), whole.cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Time-chunked long-form path on ONE GPU: the ranks of a 2- / 3- / 4-GPU run are emulated one after the other (the halo
+# exchanges are tensor copies), so the driver's single-GPU test run covers sc_griffinlim_chunk_run, the windowed
+# de-emphasis carry and the canonical sums.  tests/test_gpu_distributed.py repeats it over NCCL.
+def _emulate(world, T, n_iter, k, realse=1.0, hop=80, n_fft=400, pdb_seed=3600):
+    import torch
+    from speech_cloner_b200 import distributed as D
+    from speech_cloner_b200.audio_lib import DspPlan
+    plan = DspPlan.get(n_fft=n_fft, win_length=n_fft, hop_length=hop)
+    kw = dict(HP); kw.update(hop_length=hop, win_length=n_fft, n_fft=None)
+    base = oracle.calc_MFCC_input(synth.utterance(pdb_seed, 3.0), **kw)[2]
+    P = np.concatenate([base] * (T // base.shape[0] + 1))[:T]
+    ph = _phase0(17, (n_fft // 2 + 1, T))
+    ranks = [D.ChunkedGriffinLim(T, hop, n_fft, steps_per_exchange=k, plan=plan, world=world, rank=r) for r in range(world)]
+    P_dev = torch.from_numpy(np.ascontiguousarray(P)).cuda()
+    ph_dev = torch.from_numpy(np.ascontiguousarray(ph.T).astype(np.float32)).cuda()
+    return plan, P, ph, ranks, P_dev, ph_dev
+
+
+def _emulated_exchange(ranks, bufs, e_los, width):
+    """What ChunkedGriffinLim._exchange does over NCCL, as copies between the emulated ranks' buffers."""
+    for r, cg in enumerate(ranks):
+        if cg.hi <= cg.lo:
+            continue
+        for nb in (r - 1, r + 1):
+            if not cg._live(nb):
+                continue
+            o = ranks[nb]
+            if nb < r:      # my left halo <- the left neighbour's last `width` samples
+                bufs[r][cg.lo - e_los[r] - width: cg.lo - e_los[r]] = bufs[nb][o.hi - e_los[nb] - width: o.hi - e_los[nb]]
+            else:
+                w = min(width, cg.total - cg.hi)
+                bufs[r][cg.hi - e_los[r]: cg.hi - e_los[r] + w] = bufs[nb][o.lo - e_los[nb]: o.lo - e_los[nb] + w]
+
+
+@pytest.mark.parametrize("world,T,n_iter,k,realse", [(2, 449, 7, 3, 1.0), (3, 1200, 9, 20, 1.0), (4, 2001, 12, 4, 1.2),
+                                                     (2, 321, 4, 2, 1.0)])
+def test_chunk_run_emulated_ranks_bit_identical(al, world, T, n_iter, k, realse):
+    """Communication-avoiding chunked from_power_to_wav == the single-GPU call, bit for bit."""
+    import torch
+    from speech_cloner_b200 import _lib
+    from speech_cloner_b200 import distributed as D
+    geom = dict(hop=40, n_fft=800) if T == 321 else {}
+    plan, P, ph, ranks, P_dev, ph_dev = _emulate(world, T, n_iter, k, realse, **geom)
+    hop, n_fft = ranks[0].hop, ranks[0].n_fft
+    kw = dict(GL); kw.update(hop_length=hop, win_length=n_fft)
+    whole = al.from_power_to_wav(P, n_iter=n_iter, realse=realse, verbose=False, phase0=ph, **kw)
+    lib, st = plan._lib, torch.cuda.current_stream().cuda_stream
+    assert all(cg.hi > cg.lo for cg in ranks)
+    # ---- prologue: block partials of the rows every rank owns, "all_gather" = concatenation in rank order
+    amps = []
+    parts = []
+    for cg in ranks:
+        f_lo, f_hi = cg.frame_range(n_iters=n_iter)
+        o_lo, o_hi = cg.own_frame_range()
+        part = torch.zeros(2 * (-(-(o_hi - o_lo) // cg.align)), dtype=torch.float64, device="cuda")
+        if realse != 1.0:
+            _lib.check(lib.sc_p2a_chunk_partial(plan._h, P_dev[o_lo:].data_ptr(), o_hi - o_lo, realse, part.data_ptr(), st), "partial")
+        parts.append(part)
+    allp = torch.cat(parts).contiguous()
+    for cg in ranks:
+        f_lo, f_hi = cg.frame_range(n_iters=n_iter)
+        amp = torch.empty((f_hi - f_lo, n_fft // 2 + 1), dtype=torch.float32, device="cuda")
+        _lib.check(lib.sc_p2a_chunk_apply(plan._h, P_dev[f_lo:f_hi].contiguous().data_ptr(), f_hi - f_lo, 0.01, realse,
+                                          allp.data_ptr() if realse != 1.0 else None, allp.shape[0] // 2, amp.data_ptr(), st), "apply")
+        amps.append(amp)
+    # ---- iterations in rounds of k with emulated exchanges
+    a, b, e_los = [], [], []
+    for cg in ranks:
+        e_lo, e_hi = cg.ext_range(n_iters=n_iter)
+        a.append(torch.zeros(e_hi - e_lo, dtype=torch.float32, device="cuda")); b.append(torch.zeros_like(a[-1])); e_los.append(e_lo)
+    kk = ranks[0]._k_for(n_iter)
+    done = 0
+    while done < n_iter:
+        n = min(kk, n_iter - done)
+        for r, cg in enumerate(ranks):
+            f_lo, f_hi = cg.frame_range(n_iters=n_iter)
+            e_lo, e_hi = cg.ext_range(n_iters=n_iter)
+            cg._round(amps[r], ph_dev[f_lo:f_hi].contiguous() if done == 0 else None, f_lo, f_hi, a[r], b[r], e_lo, e_hi, n)
+        if n & 1:
+            a, b = b, a
+        done += n
+        if done < n_iter:
+            _emulated_exchange(ranks, a, e_los, min(kk, n_iter - done) * ranks[0].halo)
+    chunks = [a[r][cg.lo - e_los[r]: cg.hi - e_los[r]].contiguous() for r, cg in enumerate(ranks)]
+    # float32 Griffin-Lim state: compare against the whole-signal kernel through the public single call
+    plan1 = plan
+    from speech_cloner_b200.audio_lib import _GlLayout, griffin_lim_device
+    amp_whole = torch.empty_like(P_dev)
+    lay = _GlLayout([T], hop)
+    _lib.check(lib.sc_power_to_amp_batch(plan1._h, P_dev.data_ptr(), lay.c_frame_offsets, lay.c_frame_counts, 1, 0.01, realse,
+                                         amp_whole.data_ptr(), st), "p2a")
+    gl_whole = griffin_lim_device(plan1, amp_whole, ph_dev, lay, n_iter)[: hop * (T - 1)]
+    assert torch.equal(torch.cat(chunks), gl_whole)
+    # ---- epilogue: local responses, the left neighbour's last `win`, apply, gathered block sums, renorm
+    win = int(lib.sc_deemph_chunk_window(0.97))
+    assert win == 12
+    locs = []
+    for r, cg in enumerate(ranks):
+        n_chunks = -(-(cg.hi - cg.lo) // 256)
+        loc = torch.zeros(win + n_chunks, dtype=torch.float64, device="cuda")
+        _lib.check(lib.sc_deemph_chunk_local(plan._h, chunks[r].data_ptr(), cg.lo, cg.hi - cg.lo, cg.total, 0.97, loc[win:].data_ptr(), st), "local")
+        locs.append(loc)
+    for r in range(1, world):
+        locs[r][:win] = locs[r - 1][-win:]
+    outs, sums = [], []
+    for r, cg in enumerate(ranks):
+        out = torch.empty(cg.hi - cg.lo, dtype=torch.float64, device="cuda")
+        sm = torch.zeros(-(-(cg.hi - cg.lo) // cg.sum_block), dtype=torch.float64, device="cuda")
+        _lib.check(lib.sc_deemph_chunk_apply(plan._h, chunks[r].data_ptr(), cg.lo, cg.hi - cg.lo, cg.total, 0.97, locs[r].data_ptr(), win,
+                                             out.data_ptr(), sm.data_ptr(), st), "apply")
+        outs.append(out); sums.append(sm)
+    alls = torch.cat(sums).contiguous()
+    for r, cg in enumerate(ranks):
+        _lib.check(lib.sc_renorm_chunk(plan._h, outs[r].data_ptr(), cg.hi - cg.lo, alls.data_ptr(), alls.shape[0], cg.total, 0.045, st), "renorm")
+    got = torch.cat(outs).cpu().numpy()
+    np.testing.assert_array_equal(got, whole)                           # float64 epilogue: bit-identical too
+
+
+def test_deemphasis_windowed_carry_matches_lfilter(al):
+    """The truncated carry series of the chunked scan against scipy's sequential filter, long signal, float64 accuracy."""
+    from scipy import signal
+    rng = np.random.default_rng(5)
+    x = (0.05 * rng.standard_normal(300001)).astype(np.float32)
+    got = al.calc_inv_preemphasis(x, 0.97)
+    want = signal.lfilter([1.0], [1.0, -0.97], x.astype(np.float64))
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-13)
+    # a coefficient too close to 1 for a short window takes the sequential fallback
+    got2 = al.calc_inv_preemphasis(x[:70000], 0.9999)
+    want2 = signal.lfilter([1.0], [1.0, -0.9999], x[:70000].astype(np.float64))
+    np.testing.assert_allclose(got2, want2, rtol=1e-10, atol=1e-11)
+    # float64 input is not rounded to float32 first (scipy keeps float64)
+    x64 = x.astype(np.float64) + 1e-11
+    np.testing.assert_allclose(al.calc_inv_preemphasis(x64, 0.97), signal.lfilter([1.0], [1.0, -0.97], x64), rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(al.calc_preemphasis(x64, 0.97), signal.lfilter([1.0, -0.97], [1.0], x64), rtol=0, atol=1e-15)
+
+
+def test_zero_iterations_follow_the_reference(al):
+    P = _pdb(3400, 0.5)[:50]
+    amp = np.ones((201, 50), dtype=np.float32)
+    assert al.griffin_lim_alg(amp, 400, 80, num_iters=0, verbose=False) is None        # audio_lib.py:252 `wav = None`
+    with pytest.raises(ValueError):
+        al.from_power_to_wav(P, n_iter=0, verbose=False, **GL)

@@ -65,3 +65,39 @@ def test_synth_is_seeded_and_shaped():
     np.testing.assert_array_equal(a, b)
     assert a.dtype == np.float32 and a.shape == (16000,) and 0.05 < np.abs(a).max() < 0.2
     assert np.abs(synth.utterance(7, 1.0, ds_norm=(0.0, 10.0)) - 10 * a).max() < 1e-6
+
+
+def test_signatures_match_the_reference_source():
+    """Pinned to the reference's own source: parse /root/reference/audio_lib.py with ast (it cannot be imported here:
+    librosa / matplotlib are absent) and compare names, order and defaults of the five functions.  Skipped on the GPU
+    box, where /root/reference does not exist; tests/golden/reference_signatures.json is the travelling copy."""
+    import ast
+    import inspect
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = os.path.join(here, "golden", "reference_signatures.json")
+    names = ["calc_preemphasis", "calc_inv_preemphasis", "calc_PHN_target", "calc_MFCC_input", "griffin_lim_alg",
+             "from_power_to_wav"]
+
+    def from_source(path):
+        tree = ast.parse(open(path).read())
+        out = {}
+        for node in tree.body:
+            if isinstance(node, ast.FunctionDef) and node.name in names:
+                args = node.args.args
+                defaults = [None] * (len(args) - len(node.args.defaults)) + list(node.args.defaults)
+                out[node.name] = [[a.arg, "<required>" if d is None else repr(ast.literal_eval(d))] for a, d in zip(args, defaults)]
+        return out
+    ref_path = "/root/reference/audio_lib.py"
+    if os.path.exists(ref_path):
+        parsed = from_source(ref_path)
+        assert sorted(parsed) == sorted(names)
+        assert parsed == json.load(open(gold)), "tests/golden/reference_signatures.json is stale: rerun tests/golden/make_signatures.py"
+    want = json.load(open(gold))
+    for name in names:
+        sig = inspect.signature(getattr(al, name))
+        got = [[p.name, "<required>" if p.default is inspect.Parameter.empty else repr(p.default)] for p in sig.parameters.values()]
+        assert got[:len(want[name])] == want[name], name
+        extra = got[len(want[name]):]
+        assert all(e[0] in ("phase0",) for e in extra), f"{name}: only the documented phase0 keyword may be added, got {extra}"
