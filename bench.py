@@ -2,27 +2,35 @@
 """bench.py — audio-seconds/second of the speech-cloner DSP hot path on B200 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--precision fp64|fp32] [--no-gl] [--no-cpu]
+                    [--precision fp64|fp32] [--no-gl] [--no-gl-long] [--no-sweep] [--no-cpu] [--no-e2e]
 
 A "step" is one pass of the front-end (calc_MFCC_input, /root/reference/audio_lib.py:89-244) over
 BASELINE.json configs[1]: 256 synthetic ARCTIC-shaped utterances x 4 s at the hp/*.json settings
 (205 056 frames, 65.5 MB in, 296.1 MB out).  One JSON line is printed by rank 0:
 
-  value      whole-job audio-s/s with the waveforms already resident in HBM (CUDA events, max over ranks)
-  e2e        the same through the host-buffer pipeline: pinned H2D of every waveform and pinned D2H of the
-             three feature arrays inside the timed region
-  roofline   achieved algorithmic GB/s (1 764 B/frame) over the summed kernel time of a
-             step, against MEASURED_PEAKS.json hbm_gbs; per-kernel shares from CUDA events in the library
-  cpu_baseline   the CPU oracle (restated reference path) on this box's host cores, bounded sample
-  griffin_lim    secondary measurement, configs[2]: 64 spectrograms x 5 s, 200 iterations (test.py:87)
+  value        whole-job audio-s/s with the waveforms already resident in HBM (CUDA events, max over ranks)
+  e2e          the same through the host-buffer pipeline: pinned H2D of every waveform and pinned D2H of the
+               three feature arrays inside the timed region; pcie_* = the same bytes moved by bare pinned copies
+               (both directions at once, all ranks at once) in this run, i.e. the ceiling e2e can reach
+  roofline     achieved algorithmic GB/s (1 764 B/frame) over the summed kernel time of a
+               step, against MEASURED_PEAKS.json hbm_gbs; per-kernel shares from CUDA events in the library;
+               traffic = DRAM bytes from the committed ncu capture, reported only while the kernel sources still
+               hash to what was captured
+  cpu_baseline the CPU oracle (restated reference path) on this box's host cores, bounded sample
+  griffin_lim  configs[2]: 64 spectrograms x 5 s, 200 iterations (test.py:87), device-resident and `e2e` through
+               from_power_to_wav_batch with host arrays; long_form = configs[3]: one 20 min spectrogram time-chunked
+               over the ranks, prologue + 200 iterations + distributed epilogue + final gather inside the timed region
+  sweep_10h    configs[4]: 10 h of audio, utterance-sharded, with the final gather of the feature buffers timed
+  parity_selfcheck   sharded == single and chunked == unchunked (bit-identical) on this run's ranks
 
-Under torchrun every rank featurises its own copy of the batch (weak scaling, no data-path
-collective: utterances are independent).  `--impl reference` times the CPU oracle with
-all host cores on the same config (rank 0 only).
+Under torchrun every rank featurises its own copy of the batch (weak scaling, no data-path collective: utterances
+are independent); configs[3] and configs[4] are strong-scaling legs.  `--impl reference` times the
+CPU oracle with all host cores on the same config (rank 0 only) and prints the same metric string.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import multiprocessing as mp
 import os
@@ -49,11 +57,21 @@ import numpy as np  # noqa: E402
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# ONE metric / workload string for both arms: the driver divides the arms only when they match
+METRIC = "audio-seconds/second, front-end (calc_MFCC_input)"
+UNIT = "audio-s/s"
+WORKLOAD = ("frontend configs[1]: 256 x 4 s ARCTIC-shaped utterances per GPU, hp/ds_dec_cfg_d.json "
+            "(sr 16000, n_fft 400, hop 80, 80 mels, 40 MFCC + delta)")
+
 N_UTTS, SECONDS, SR = 256, 4.0, 16000
 GL_UTTS, GL_SECONDS, GL_ITERS = 64, 5.0, 200
+T_LONG = 240001                                            # configs[3]: 20 min at hop 80
 FE_BYTES_PER_FRAME = 4 * (80 + 201 + 80 + 80)            # wav in + three outputs
 GL_BYTES_PRIMARY = 4 * 201 + 8 * 201 + 8 * 201           # complex64 spectrogram state
 GL_BYTES_STRICT = 4 * 201 + 2 * 4 * 80                   # waveform state (what the kernel moves)
+GL_KW = dict(P_dB_norm_factor=0.01, pre_emphasis=0.97, hop_length=80, win_length=400, mean_abs_amp_norm=0.045,
+             realse=1.0)
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_traffic.json")
 
 
 def hbm_peak():
@@ -62,6 +80,32 @@ def hbm_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def kernel_source_hash() -> str:
+    """sha256 over the kernel sources and the header: pins profiles/r02_traffic.json to the code it was captured from."""
+    h = hashlib.sha256()
+    base = os.path.join(ROOT, "speech_cloner_b200", "csrc")
+    for name in sorted(os.listdir(base)):
+        if name.endswith((".cu", ".cuh")):
+            h.update(name.encode())
+            h.update(open(os.path.join(base, name), "rb").read())
+    h.update(open(os.path.join(ROOT, "include", "speechdsp.h"), "rb").read())
+    return h.hexdigest()
+
+
+def load_traffic():
+    """(table, note): the committed ncu DRAM-byte table if it still belongs to the current kernel sources, else {}."""
+    try:
+        with open(TRAFFIC_FILE) as f:
+            tab = json.load(f)
+    except Exception:
+        return {}, "no committed ncu traffic capture for this round (profiles/r02_traffic.json)"
+    want, have = tab.get("_src_sha256"), kernel_source_hash()
+    if want != have:
+        return {}, (f"profiles/r02_traffic.json was captured from other kernel sources (sha256 {str(want)[:12]} != "
+                    f"{have[:12]}): stale, not reported")
+    return tab, f"DRAM read+write bytes per launch, ncu --set full, profiles/r02_traffic.json (source sha256 {have[:12]})"
 
 
 # ------------------------------------------------------------------------------ clocks
@@ -135,22 +179,20 @@ def cpu_frontend_single(wavs):
 def cpu_gl_single(P, phase0, iters):
     from oracle import audio_lib_oracle as oracle
     t = time.perf_counter()
-    oracle.from_power_to_wav(P, P_dB_norm_factor=0.01, pre_emphasis=0.97, hop_length=80, win_length=400,
-                             mean_abs_amp_norm=0.045, n_iter=iters, realse=1.0, verbose=False, phase0=phase0)
+    oracle.from_power_to_wav(P, n_iter=iters, verbose=False, phase0=phase0, **GL_KW)
     return time.perf_counter() - t
 
 
 def run_reference(args):
     """`--impl reference`: the reference's CPU path (oracle restatement; librosa is not installable) with
-    every host core, one utterance per task, BLAS threads pinned to 1."""
+    every host core, one utterance per task, BLAS threads pinned to 1, on ALL 256 utterances of the same config."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from speech_cloner_b200 import synth
     cores = os.cpu_count() or 1
-    sample_n = 64
-    wavs = synth.batch(2, sample_n, SECONDS)
-    audio_s = sample_n * SECONDS
+    wavs = synth.batch(2, N_UTTS, SECONDS)
+    audio_s = N_UTTS * SECONDS
     with mp.get_context("fork").Pool(cores) as pool:
         for _ in range(max(args.warmup, 1)):
             pool.map(_oracle_utt, wavs, chunksize=1)
@@ -159,15 +201,16 @@ def run_reference(args):
             pool.map(_oracle_utt, wavs, chunksize=1)
         dt = (time.perf_counter() - t) / args.steps
     val = audio_s / dt
-    sample = f"{sample_n} of the 256 utterances x {SECONDS:g} s per step, multiprocessing.Pool({cores})"
+    sample = f"all {N_UTTS} utterances x {SECONDS:g} s per step (the full config), multiprocessing.Pool({cores})"
     emit({
-        "impl": "reference", "metric": "audio-seconds/second, front-end (calc_MFCC_input)", "value": val,
-        "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": METRIC, "value": val,
+        "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "frontend configs[1]: 256 x 4 s ARCTIC-shaped, hp/ds_dec_cfg_d.json", "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": WORKLOAD, "same_config": True, "sample": sample,
+                   "note": "the reference is one single-process CPU job whatever --gpus says; value is its whole-job rate"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
 
@@ -179,12 +222,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
-    ap.add_argument("--no-gl", action="store_true")
+    ap.add_argument("--no-gl", action="store_true", help="skip every Griffin-Lim leg")
+    ap.add_argument("--no-gl-long", action="store_true", help="skip the chapter-length chunked Griffin-Lim (configs[3])")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the 10 h featurization sweep (configs[4])")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--gl-long", action="store_true", help="also time the chapter-length chunked Griffin-Lim (configs[3])")
-    ap.add_argument("--sweep", action="store_true", help="also time the 10 h featurization sweep (configs[4]), utterance-sharded")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pipeline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs (profiling runs)")
     ap.add_argument("--no-probe", action="store_true", help="skip the 1.2 s clock probe loop (profiling runs)")
+    ap.add_argument("--no-selfcheck", action="store_true", help="skip the distributed parity self-check")
+    ap.add_argument("--gl-long", action="store_true", help=argparse.SUPPRESS)    # round-1 spelling: now the default
+    ap.add_argument("--sweep", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -193,17 +239,17 @@ def main():
     import torch
     import torch.distributed as dist
     from speech_cloner_b200 import audio_lib as al
+    from speech_cloner_b200 import distributed as D
     from speech_cloner_b200 import synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    cpu_bind = None
+    bind = {"action": "not attempted", "why": "single rank"}
     if world > 1:
         # one process per GPU: keep the rank (and the pinned buffers it is about to allocate) on the GPU's NUMA node
-        from speech_cloner_b200 import distributed as D
-        cpu_bind = D.bind_to_gpu_cpus(local)
+        bind = D.bind_report(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -218,7 +264,20 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def timed(fn, reps=1):
+        """max over ranks of the device time of fn() (CUDA events on the current stream, barrier both sides)."""
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        res = None
+        for _ in range(reps):
+            res = fn()
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b) / reps), res
+
     peak, peak_src = hbm_peak()
+    traffic_tab, traffic_note = load_traffic()
     hp = dict(synth.HP_ENC)
     plan_kw = dict(sr=hp["sr"], n_fft=400, win_length=400, hop_length=80, n_mels=80, n_mfcc=40, window="hann",
                    pre_emphasis=0.97, mfcc_normaleze_first_mfcc=True, mfcc_norm_factor=0.01, calc_mfcc_derivate=True,
@@ -266,30 +325,27 @@ def main():
     plan.profile(False)
     prof /= n_prof
     kern_ms = float(prof.sum())
-    names = ["gain: k_fe_setup + k_abs_pairwise4 + k_gain_finalize", "pass A: k_fe_pass_a_ws", "pass B: k_fe_c00 + k_fe_pass_b3"]
+    names = ["gain: k_abs_pairwise4 + k_gain_finalize (k_fe_setup only when the layout changes)", "pass A: k_fe_pass_a_ws",
+             "pass B: k_fe_c00 + k_fe_pass_b3"]
+    tkeys = ["gain", "pass_a", "pass_b"]
     top = int(np.argmax(prof))
     fe_bytes = FE_BYTES_PER_FRAME * frames
-    try:                                   # DRAM bytes per launch from the committed ncu --set full capture
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            traffic_tab = json.load(f)
-    except Exception:
-        traffic_tab = {}
     achieved = fe_bytes / (kern_ms * 1e-3) / 1e9
+    kbytes = [320, 1444, 2568]
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": (sum(traffic_tab.get(n, float("nan")) for n in names) if traffic_tab else None),
-        "traffic_note": "DRAM read+write bytes of one step (all kernels), ncu --set full, profiles/r01_traffic.json; "
-                        "algorithmic bytes of the step: %d" % fe_bytes,
-        "kernel_traffic": traffic_tab.get(names[top]),
+        "traffic": (sum(traffic_tab.get(k, float("nan")) for k in tkeys) if traffic_tab else None),
+        "traffic_note": traffic_note + "; algorithmic bytes of the step: %d" % fe_bytes,
+        "kernel_traffic": traffic_tab.get(tkeys[top]),
         "peak_source": peak_src,
         "definition": "1764 B/frame x frames of one step / summed device time of the step's kernels",
         "kernel": names[top],
         # the dominant kernel against its own algorithmic bytes: gain reads the audio once
         # (320 B/frame), pass A reads it again and writes the raw dB tiles (320 + 1124), pass B re-reads and rewrites
         # (1124 + 1444)
-        "kernel_algorithmic_bytes_per_frame": [320, 1444, 2568][top],
-        "kernel_achieved": [320, 1444, 2568][top] * frames / (float(prof[top]) * 1e-3) / 1e9,
-        "kernel_frac": [320, 1444, 2568][top] * frames / (float(prof[top]) * 1e-3) / 1e9 / peak,
+        "kernel_algorithmic_bytes_per_frame": kbytes[top],
+        "kernel_achieved": kbytes[top] * frames / (float(prof[top]) * 1e-3) / 1e9,
+        "kernel_frac": kbytes[top] * frames / (float(prof[top]) * 1e-3) / 1e9 / peak,
         "kernels": {n: {"ms": float(m), "share": float(m / kern_ms)} for n, m in zip(names, prof)},
         "step_ms_back_to_back": ms_step,
     }
@@ -301,15 +357,8 @@ def main():
         plan32 = al.DspPlan(**kw32)
         for _ in range(args.warmup):
             al.frontend_device(plan32, wav_dev, lay, out)
-        barrier()
-        a32, b32 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a32.record()
-        for _ in range(args.steps):
-            al.frontend_device(plan32, wav_dev, lay, out)
-        b32.record()
-        barrier()
-        ms32 = max_over_ranks(a32.elapsed_time(b32) / args.steps)
-        alt = {"fft_precision": "fp32", "ms_per_step": ms32, "value": world * audio_s / (ms32 * 1e-3), "unit": "audio-s/s",
+        ms32, _ = timed(lambda: al.frontend_device(plan32, wav_dev, lay, out), args.steps)
+        alt = {"fft_precision": "fp32", "ms_per_step": ms32, "value": world * audio_s / (ms32 * 1e-3), "unit": UNIT,
                "roofline_frac": fe_bytes / (ms32 * 1e-3) / 1e9 / peak,
                "note": "not the default: bins 70-80 dB below the utterance maximum can deviate by up to ~5e-5"}
         del plan32
@@ -335,12 +384,37 @@ def main():
             pipe.run()
         torch.cuda.synchronize()
         e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
-        e2e = {"value": world * audio_s / e2e_s, "unit": "audio-s/s", "ms_per_step": e2e_s * 1e3,
+        # PCIe ceiling measured in this run: the step's H2D and D2H bytes as bare pinned copies on two streams, both
+        # directions at once, every rank at once (ranks of one node share the host's PCIe-to-memory bandwidth)
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def bare_copies():
+            with torch.cuda.stream(s_up):
+                pipe.wav_dev.copy_(pipe.wav_host, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                for h, d in zip(pipe.out_host, pipe.out_dev):
+                    h.copy_(d, non_blocking=True)
+        for _ in range(2):
+            bare_copies()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            bare_copies()
+            s_up.synchronize(); s_dn.synchronize()
+        pcie_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+        e2e = {"value": world * audio_s / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
                "h2d_bytes_per_step": int(pipe.h2d_bytes), "d2h_bytes_per_step": int(pipe.d2h_bytes),
-               "path": "FrontendPipeline.run(): 8 utterance chunks over 3 streams, pinned host buffers"}
+               "path": "FrontendPipeline.run(): 8 utterance chunks over 3 streams, pinned host buffers",
+               "pcie_ms_per_step": pcie_s * 1e3,
+               "pcie_ceiling_gbs": world * (pipe.h2d_bytes + pipe.d2h_bytes) / pcie_s / 1e9,
+               "pcie_ceiling_value": world * audio_s / pcie_s,
+               "frac_of_pcie": pcie_s / e2e_s,
+               "pcie_note": f"the same {pipe.h2d_bytes + pipe.d2h_bytes} bytes per rank as bare pinned copies, both directions and "
+                            f"all {world} rank(s) concurrently, measured in this run: e2e cannot exceed pcie_ceiling_value"}
 
     # ---- Griffin-Lim, configs[2]
     gl = None
+    Ps_host = phs_host = None
     if not args.no_gl:
         gl_wavs = synth.batch(3 + 10 * rank, GL_UTTS, GL_SECONDS)
         feats = al.calc_MFCC_input_batch(gl_wavs, return_device=True, **hp)
@@ -349,10 +423,13 @@ def main():
         gplan = al.DspPlan.get(n_fft=400, win_length=400, hop_length=80)
         p_dev = torch.zeros((glay.frame_offsets[-1], 201), dtype=torch.float32, device="cuda")
         ph_dev = torch.zeros_like(p_dev)
+        phs_host = []
         for i, (P, o) in enumerate(zip(Ps, glay.frame_offsets)):
             p_dev[o:o + 1000] = P
             np.random.seed(3000 + i)
-            ph_dev[o:o + 1000] = torch.from_numpy((np.pi * np.random.rand(201, 1000)).T.astype(np.float32)).cuda()
+            phs_host.append(np.pi * np.random.rand(201, 1000))                # float64 (bins, T), like audio_lib.py:255
+            ph_dev[o:o + 1000] = torch.from_numpy(phs_host[-1].T.astype(np.float32)).cuda()
+        Ps_host = [P.cpu().numpy() for P in Ps]
         amp_dev = torch.empty_like(p_dev)
         wav_out = torch.empty(glay.sample_offsets[-1], dtype=torch.float32, device="cuda")
         out64 = torch.empty(glay.sample_offsets[-1], dtype=torch.float64, device="cuda")
@@ -390,66 +467,147 @@ def main():
         gl_audio = GL_UTTS * 80 * 999 / SR
         gl = {"workload": "configs[2]: 64 x (1000, 201) spectrograms, 200 iterations, fixed phase0, "
                           "mean_abs_amp_norm 0.045, realse 1.0 (test.py:148-156)",
-              "value": world * gl_audio / (gl_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": gl_ms,
+              "value": world * gl_audio / (gl_ms * 1e-3), "unit": UNIT, "ms_per_step": gl_ms,
               "ms_per_iteration": iter_ms, "l2": "flushed between timed steps; state stays L2-resident inside a step",
               "roofline": {"bound": "hbm", "kernel": "k_gl_iter_persist", "peak": peak, "unit": "GB/s",
                            "achieved": GL_BYTES_PRIMARY * fr / (iter_ms * 1e-3) / 1e9,
                            "frac": GL_BYTES_PRIMARY * fr / (iter_ms * 1e-3) / 1e9 / peak,
-                           "definition": "4020 B/frame-iteration (complex64 spectrogram state, SURVEY.md §8(d))",
+                           "definition": "4020 B/frame-iteration (complex64 spectrogram state, SURVEY.md §8(d)); bookkeeping "
+                                         "figure: the kernel keeps the waveform state, see strict_*",
                            "strict_achieved": GL_BYTES_STRICT * fr / (iter_ms * 1e-3) / 1e9,
                            "strict_frac": GL_BYTES_STRICT * fr / (iter_ms * 1e-3) / 1e9 / peak,
                            "strict_definition": "1444 B/frame-iteration (waveform state: what the kernel moves)",
-                           "traffic": traffic_tab.get("k_gl_iter_persist")}}
+                           "traffic": traffic_tab.get("gl_iter")}}
+        # ---- the same through the public API with HOST arrays (from_power_to_wav_batch: pinned staging, one H2D per
+        # array kind, device transpose of the float64 phases, pinned D2H of the float64 waveforms)
+        if not args.no_e2e:
+            def gl_public():
+                return al.from_power_to_wav_batch(Ps_host, n_iter=GL_ITERS, verbose=False, phase0s=phs_host, n_fft=None, **GL_KW)
+            gl_public()
+            barrier()
+            reps = 2
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                res = gl_public()
+            gl_e2e_s = max_over_ranks((time.perf_counter() - t0) / reps)
+            gl["e2e"] = {"value": world * gl_audio / gl_e2e_s, "unit": UNIT, "ms_per_step": gl_e2e_s * 1e3,
+                         "h2d_bytes_per_step": int(sum(P.nbytes for P in Ps_host) + sum(p.nbytes for p in phs_host)),
+                         "d2h_bytes_per_step": int(sum(r.nbytes for r in res)),
+                         "path": "audio_lib.from_power_to_wav_batch(list of host (1000, 201) float32 maps, host float64 phases) -> "
+                                 "host float64 waveforms"}
 
-    # ---- long-form Griffin-Lim, configs[3]: one ~20 min spectrogram time-chunked over the ranks
-    if gl is not None and args.gl_long:
-        from speech_cloner_b200 import distributed as D
-        T_long = 240001
-        cg = D.ChunkedGriffinLim(T_long, 80, 400)
-        f_lo, f_hi = cg.frame_range()
-        reps = -(-(f_hi - f_lo) // 1000)
-        amp_l = amp_dev[:1000].repeat(reps, 1)[: f_hi - f_lo].contiguous()      # tiled decoder-shaped magnitudes
-        ph_l = ph_dev[:1000].repeat(reps, 1)[: f_hi - f_lo].contiguous()
-        cg.run(amp_l, ph_l, 3)
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); chunk = cg.run(amp_l, ph_l, GL_ITERS); b.record()
-        barrier()
-        long_ms = max_over_ranks(a.elapsed_time(b))
-        gl["long_form"] = {"workload": "configs[3]: one (240001, 201) spectrogram (20 min), 200 iterations, time-chunked "
-                                       f"over {world} rank(s), 480-sample halo exchange per iteration",
-                           "ms_per_step": long_ms, "value": (80 * (T_long - 1) / SR) / (long_ms * 1e-3), "unit": "audio-s/s",
-                           "scaling": "strong"}
+    # ---- long-form Griffin-Lim, configs[3]: one ~20 min spectrogram time-chunked over the ranks.  Timed region =
+    # prologue (power -> amplitude) + 200 iterations with a halo exchange every k + distributed epilogue + final gather
+    long_full = None
+    if gl is not None and not args.no_gl_long:
+        cg = D.ChunkedGriffinLim(T_LONG, 80, 400, steps_per_exchange=20)
+        f_lo, f_hi = cg.frame_range(n_iters=GL_ITERS)
+        idx = torch.arange(f_lo, f_hi, device="cuda") % 1000
+        p_l = p_dev[:1000][idx].contiguous()                                   # tiled decoder-shaped power-dB rows
+        ph_l = ph_dev[:1000][idx].contiguous()
 
-    # ---- dataset-scale sweep, configs[4]: 10 h = 6000 x 3 s (TIMIT-shaped, gain 10) + 4500 x 4 s, sharded by frames
+        def long_step():
+            y = cg.from_power_to_wav(p_l, ph_l, n_iter=GL_ITERS, **{k: v for k, v in GL_KW.items()
+                                                                    if k not in ("hop_length", "win_length")})
+            return cg.gather(y, dst=None)
+        long_step()
+        long_ms, long_full = timed(long_step)
+        n_exch = -(-GL_ITERS // cg._k_for(GL_ITERS)) - 1 if world > 1 else 0
+        gl["long_form"] = {"workload": f"configs[3]: one ({T_LONG}, 201) spectrogram (20 min), 200 iterations, time-chunked over "
+                                       f"{world} rank(s); timed: sc_p2a_chunk_* + {GL_ITERS} iterations ({n_exch} halo exchanges of "
+                                       f"{cg._k_for(GL_ITERS) * cg.halo} samples) + distributed de-emphasis / renorm + all_gather of the "
+                                       "float64 waveform",
+                           "ms_per_step": long_ms, "value": (80 * (T_LONG - 1) / SR) / (long_ms * 1e-3), "unit": UNIT,
+                           "scaling": "strong", "steps_per_exchange": cg._k_for(GL_ITERS), "halo_samples_per_iteration": cg.halo}
+
+    # ---- dataset-scale sweep, configs[4]: 10 h = 6000 x 3 s (TIMIT-shaped, gain 10) + 4500 x 4 s, sharded by frames,
+    # compute + the one final gather of the three feature buffers
     sweep = None
-    if args.sweep:
-        from speech_cloner_b200 import distributed as D
+    if not args.no_sweep:
         lens = [48000] * 6000 + [64000] * 4500
-        mine = D.shard_by_frames(lens, world, 80)[rank]
+        shards = D.shard_by_frames(lens, world, 80)
+        mine = shards[rank]
         pool3 = synth.batch(5, 16, 3.0, ds_norm=(0.0, 10.0))
         pool4 = wavs[:16]
         slay = al.FrontendLayout([lens[i] for i in mine], 80)
+        rows = [al.FrontendLayout([lens[i] for i in s], 80).total_frames for s in shards]
         sdev = torch.empty(slay.total_samples, dtype=torch.float32, device="cuda")
         p3 = [torch.from_numpy(w).cuda() for w in pool3]
         p4 = [torch.from_numpy(w).cuda() for w in pool4]
         for k, (i, o) in enumerate(zip(mine, slay.sample_offsets)):
             src = p3[i % 16] if lens[i] == 48000 else p4[i % 16]
             sdev[o:o + lens[i]] = src                                     # 16 distinct utterances per shape, tiled
-        sout = al.frontend_device(plan, sdev, slay)
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(3):
+        # outputs padded to the largest shard so the gather needs no staging copy
+        widths = (plan.mfcc_width, plan.n_mels, plan.n_bins)
+        sout = tuple(torch.empty((max(rows), w), dtype=torch.float32, device="cuda") for w in widths)
+        gathered = tuple(torch.empty((world * max(rows), w), dtype=torch.float32, device="cuda") for w in widths) if world > 1 else None
+
+        def sweep_compute():
             al.frontend_device(plan, sdev, slay, sout)
-        b.record()
-        barrier()
-        sw_ms = max_over_ranks(a.elapsed_time(b) / 3)
+
+        def sweep_gather():
+            if world > 1:
+                for g, s in zip(gathered, sout):
+                    dist.all_gather_into_tensor(g, s)
+
+        def sweep_all():
+            sweep_compute(); sweep_gather()
+        sweep_all()
+        sw_c, _ = timed(sweep_compute, 3)
+        sw_all, _ = timed(sweep_all, 3)
+        gbytes = 4 * sum(widths) * max(rows) * (world - 1)                # bytes each rank receives
         sweep = {"workload": "configs[4]: 10 h = 6000 x 3 s + 4500 x 4 s, utterances sharded by frame count (LPT) over "
-                             f"{world} rank(s), device resident, 16 distinct synthetic utterances per shape tiled",
-                 "ms_per_pass": sw_ms, "value": 36000.0 / (sw_ms * 1e-3), "unit": "audio-s/s", "scaling": "strong",
-                 "frac_hbm": FE_BYTES_PER_FRAME * (6000 * 601 + 4500 * 801) / world / (sw_ms * 1e-3) / 1e9 / peak}
-        del sdev, sout
+                             f"{world} rank(s), device resident, 16 distinct synthetic utterances per shape tiled; timed: front-end "
+                             "of the shard + all_gather of the three packed feature buffers (the one collective of the path)",
+                 "ms_per_pass": sw_all, "ms_compute": sw_c, "ms_gather": sw_all - sw_c,
+                 "value": 36000.0 / (sw_all * 1e-3), "value_compute_only": 36000.0 / (sw_c * 1e-3), "unit": UNIT,
+                 "scaling": "strong", "gather_bytes_received_per_rank": int(gbytes),
+                 "gather_gbs_per_rank": (gbytes / ((sw_all - sw_c) * 1e-3) / 1e9) if world > 1 and sw_all > sw_c else None,
+                 "frac_hbm_compute": FE_BYTES_PER_FRAME * (6000 * 601 + 4500 * 801) / world / (sw_c * 1e-3) / 1e9 / peak}
+        del sdev, sout, gathered
+
+    # ---- distributed parity self-check on this run's ranks (the 1-GPU test run cannot see these)
+    selfcheck = None
+    if not args.no_selfcheck and gl is not None:
+        selfcheck = {}
+        try:
+            # (1) sharded == single, bit for bit
+            sw = [synth.utterance(900 + i, s) for i, s in enumerate([1.0, 0.4, 2.0, 0.7, 1.3, 0.2, 0.9, 3.0])]
+            got = D.featurize_sharded(sw, gather=True, return_device=True, **hp)
+            want = al.calc_MFCC_input_batch(sw, return_device=True, **hp)
+            ok1 = all(torch.equal(a, b) for g, w in zip(got, want) for a, b in zip(g, w))
+            selfcheck["sharded_equals_single"] = bool(ok1)
+            # (2) chunked == unchunked at T = 2001 (realse 1.2 exercises the distributed prologue) ...
+            def unchunked(T, n_iter, realse):
+                ii = torch.arange(T, device="cuda") % 1000
+                kw = dict(GL_KW); kw["realse"] = realse
+                return al.from_power_to_wav_batch([p_dev[:1000][ii]], n_iter=n_iter, verbose=False, n_fft=None,
+                                                  phase0s=[ph_dev[:1000][ii].t()], return_device=True, **kw)[0]
+
+            def chunked(T, n_iter, realse, k):
+                c = D.ChunkedGriffinLim(T, 80, 400, steps_per_exchange=k)
+                lo_f, hi_f = c.frame_range(n_iters=n_iter)
+                ii = torch.arange(lo_f, hi_f, device="cuda") % 1000
+                y = c.from_power_to_wav(p_dev[:1000][ii].contiguous(), ph_dev[:1000][ii].contiguous(), P_dB_norm_factor=0.01,
+                                        pre_emphasis=0.97, mean_abs_amp_norm=0.045, n_iter=n_iter, realse=realse)
+                return c.gather(y, dst=None)
+            ok2 = bool(torch.equal(chunked(2001, 25, 1.2, 4), unchunked(2001, 25, 1.2)))
+            selfcheck["chunked_equals_unchunked_T2001"] = ok2
+            # ... and at the full T = 240 001 on the waveform the timed long-form step produced
+            ok3 = None
+            if long_full is not None:
+                ok3 = bool(torch.equal(long_full, unchunked(T_LONG, GL_ITERS, 1.0)))
+                selfcheck["chunked_equals_unchunked_T240001"] = ok3
+            flags = torch.tensor([int(ok1), int(ok2), int(ok3 is not False)], device="cuda")
+            if world > 1:
+                dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+            selfcheck["all_ranks"] = bool(flags.min().item() == 1)
+            selfcheck["result"] = "ok" if selfcheck["all_ranks"] else "MISMATCH"
+        except Exception as e:                                   # never lose the bench line to a check
+            selfcheck["result"] = f"error: {type(e).__name__}: {e}"
+        selfcheck["ranks"] = world
+        selfcheck["what"] = ("bit-identity (torch.equal) of featurize_sharded vs one batch call, and of the time-chunked "
+                             "from_power_to_wav (NCCL halo exchanges, distributed prologue / epilogue, gather) vs the single-GPU call")
 
     clocks = None
     if sampler:
@@ -462,33 +620,29 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v = cpu_frontend_single(wavs)
-        cpu = {"value": v, "unit": "audio-s/s", "cores": 1, "kind": "port", "host_cores_available": os.cpu_count(),
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "host_cores_available": os.cpu_count(),
                "sample": "all 256 utterances x 4 s once, sequential single-process loop like TIMIT_reader.py:169 "
                          "(oracle/audio_lib_oracle.py; librosa itself is not installable here)"}
         if gl is not None:
-            P = Ps[0].cpu().numpy()
-            np.random.seed(3000)
-            ph = np.pi * np.random.rand(201, 1000)
             it = 10
-            dt = cpu_gl_single(P, ph, it)
-            gl["cpu_baseline"] = {"value": (80 * 999 / SR) / (dt * GL_ITERS / it), "unit": "audio-s/s", "cores": 1,
+            dt = cpu_gl_single(Ps_host[0], phs_host[0], it)
+            gl["cpu_baseline"] = {"value": (80 * 999 / SR) / (dt * GL_ITERS / it), "unit": UNIT, "cores": 1,
                                   "kind": "port", "sample": f"1 spectrogram x 5 s, {it} iterations timed, scaled linearly to 200"}
 
     if rank == 0:
         line = {
-            "metric": "audio-seconds/second, front-end (calc_MFCC_input: STFT -> power dB, mel dB, MFCC+delta)",
-            "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC,
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 FFT butterflies, f32 elsewhere" if args.precision == "fp64" else "f32",
             "data": "synthetic",
-            "config": {"workload": "frontend configs[1]: 256 x 4 s ARCTIC-shaped utterances per GPU, hp/ds_dec_cfg_d.json "
-                                   "(sr 16000, n_fft 400, hop 80, 80 mels, 40 MFCC + delta)",
+            "config": {"workload": WORKLOAD, "same_config": True,
                        "frames_per_step_per_gpu": frames, "fft_precision": args.precision,
                        "l2": "inputs+outputs (361.6 MB) larger than L2, no flush",
                        "parallelism": f"utterance shards, {world} rank(s), no data-path collective",
-                       "cpu_binding_rank0": (f"{len(cpu_bind)} cores local to the GPU (NVML)" if cpu_bind else "none")},
+                       "cpu_binding_rank0": f"{bind['action']}: {bind['why']}"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "frontend_fp32_mode": alt, "griffin_lim": gl, "sweep_10h": sweep,
+            "frontend_fp32_mode": alt, "griffin_lim": gl, "sweep_10h": sweep, "parity_selfcheck": selfcheck,
         }
         emit(line)
     if world > 1:

@@ -552,12 +552,27 @@ def griffin_lim_batch(amps, win_length, hop_length, num_iters=300, n_fft=None, p
     return outs if return_device else [w.cpu().numpy() for w in outs]
 
 
+_PACK_POOL = None
+
+
+def _pack_pool():
+    """Small thread pool for packing host arrays into pinned staging buffers (NumPy copies release the GIL)."""
+    global _PACK_POOL
+    if _PACK_POOL is None:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        _PACK_POOL = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) // 2)))
+    return _PACK_POOL
+
+
 def _stage_rows(items, layout, n_bins, torch, transpose_from_freq_major: bool, lib):
     """List of per-utterance arrays / tensors -> one packed time-major float32 CUDA buffer [rows][n_bins].
 
-    Host arrays travel in ONE pinned staging buffer and one asynchronous copy (the per-utterance ``.cuda()`` calls of
-    round 1 cost more than the Griffin-Lim prologue they fed).  ``transpose_from_freq_major``: the items are
-    (n_bins, T) in the reference's orientation (float32 or float64) and are transposed on the device.
+    Host arrays travel through ONE pinned staging buffer: groups of utterances are packed by a few threads and each
+    group's asynchronous H2D copy (and device transposes) is queued as soon as it is packed, so packing, PCIe and the
+    transposes overlap (the per-utterance ``.cuda()`` calls of round 1 cost more than the Griffin-Lim prologue they
+    fed).  ``transpose_from_freq_major``: the items are (n_bins, T) in the reference's orientation (float32 or
+    float64) and are transposed on the device.
     """
     rows = layout.frame_offsets[-1]
     dst = torch.zeros((rows, n_bins), dtype=torch.float32, device="cuda")
@@ -570,13 +585,21 @@ def _stage_rows(items, layout, n_bins, torch, transpose_from_freq_major: bool, l
                 dst[o:o + t] = x.to(device="cuda", dtype=torch.float32)
         return dst
     arrs = [x.cpu().numpy() if _is_tensor(x) else np.asarray(x) for x in items]
+    n = len(arrs)
+    groups = [(g, min(n, g + max(1, -(-n // 8)))) for g in range(0, n, max(1, -(-n // 8)))]
+    pool = _pack_pool()
     if not transpose_from_freq_major:
         host = torch.empty((rows, n_bins), dtype=torch.float32, pin_memory=True)
         hv = host.numpy()
-        for a, o, o1, t in zip(arrs, layout.frame_offsets, layout.frame_offsets[1:], layout.frames):
-            hv[o:o + t] = a
+
+        def pack(i):
+            o, o1, t = layout.frame_offsets[i], layout.frame_offsets[i + 1], layout.frames[i]
+            hv[o:o + t] = arrs[i]
             hv[o + t:o1] = 0.0
-        dst.copy_(host, non_blocking=True)
+        for g0, g1 in groups:
+            list(pool.map(pack, range(g0, g1)))
+            r0, r1 = layout.frame_offsets[g0], layout.frame_offsets[g1]
+            dst[r0:r1].copy_(host[r0:r1], non_blocking=True)
         return dst
     f64 = any(a.dtype == np.float64 for a in arrs)
     dt_np, dt_t = (np.float64, torch.float64) if f64 else (np.float32, torch.float32)
@@ -584,13 +607,17 @@ def _stage_rows(items, layout, n_bins, torch, transpose_from_freq_major: bool, l
     for t in layout.frames:
         offs.append(offs[-1] + t * n_bins)
     host = torch.empty(offs[-1], dtype=dt_t, pin_memory=True)
+    src = torch.empty(offs[-1], dtype=dt_t, device="cuda")
     hv = host.numpy()
-    for a, o, t in zip(arrs, offs, layout.frames):
-        hv[o:o + t * n_bins] = np.ascontiguousarray(a, dtype=dt_np).reshape(-1)
-    src = host.to("cuda", non_blocking=True)
-    for o, fo, t in zip(offs, layout.frame_offsets, layout.frames):
-        _lib.check(lib.sc_transpose_to_f32(src.data_ptr() + o * src.element_size(), int(f64), n_bins, t,
-                                           dst.data_ptr() + fo * n_bins * 4, st), "sc_transpose_to_f32")
+
+    def pack_t(i):
+        hv[offs[i]:offs[i + 1]].reshape(n_bins, layout.frames[i])[...] = arrs[i]
+    for g0, g1 in groups:
+        list(pool.map(pack_t, range(g0, g1)))
+        src[offs[g0]:offs[g1]].copy_(host[offs[g0]:offs[g1]], non_blocking=True)
+        for i in range(g0, g1):
+            _lib.check(lib.sc_transpose_to_f32(src.data_ptr() + offs[i] * src.element_size(), int(f64), n_bins, layout.frames[i],
+                                               dst.data_ptr() + layout.frame_offsets[i] * n_bins * 4, st), "sc_transpose_to_f32")
     return dst
 
 

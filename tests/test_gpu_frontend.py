@@ -256,19 +256,19 @@ def test_same_layout_reuses_tables_and_results_do_not_change(al):
     dev = torch.zeros(lay.total_samples, dtype=torch.float32, device="cuda")
     for w, o in zip(wavs, lay.sample_offsets):
         dev[o:o + len(w)] = torch.from_numpy(w).cuda()
+    def same(x, y):          # rows between utterances (16-byte alignment padding) are never written: compare real rows
+        return all(torch.equal(p[o:o + t], q[o:o + t]) for p, q in zip(x, y) for o, t in zip(lay.frame_offsets, lay.frames))
     al.launch_count_reset()
     first = [t.clone() for t in al.frontend_device(plan, dev, lay)]
     n1 = al.launch_count()
     second = al.frontend_device(plan, dev, lay)
     n2 = al.launch_count() - n1
     assert n2 == n1 - 1
-    for p, q in zip(first, second):
-        assert torch.equal(p, q)
+    assert same(first, second)
     lay2 = al.FrontendLayout(lens[:2], 80)
     al.frontend_device(plan, dev, lay2)
     third = al.frontend_device(plan, dev, lay)
-    for p, q in zip(first, third):
-        assert torch.equal(p, q)
+    assert same(first, third)
 
 
 def test_no_allocation_after_reserve(al):
@@ -333,7 +333,8 @@ def test_plan_is_single_threaded_and_ordered_across_streams(al):
         out_b = al.frontend_device(plan, dev, lay)
     torch.cuda.synchronize()
     for p, q, r in zip(ref, out_a, out_b):
-        assert torch.equal(p, q) and torch.equal(p, r)
+        for o, t in zip(lay.frame_offsets, lay.frames):
+            assert torch.equal(p[o:o + t], q[o:o + t]) and torch.equal(p[o:o + t], r[o:o + t])
     # the reference-signature functions are thread-safe: the plan cache is keyed by thread
     y = synth.utterance(7, 0.5)
     want = al.calc_MFCC_input(y, **HP)
