@@ -500,11 +500,17 @@ def main():
     # prologue (power -> amplitude) + 200 iterations with a halo exchange every k + distributed epilogue + final gather
     long_full = None
     if gl is not None and not args.no_gl_long:
+        # ONE signal for all ranks: rank 0's first decoder-shaped map and phase, tiled to 20 min (the per-rank batches
+        # above use different seeds per rank, so they cannot be mixed into one spectrogram)
+        p1000, ph1000 = p_dev[:1000].clone(), ph_dev[:1000].clone()
+        if world > 1:
+            dist.broadcast(p1000, src=0)
+            dist.broadcast(ph1000, src=0)
         cg = D.ChunkedGriffinLim(T_LONG, 80, 400, steps_per_exchange=20)
         f_lo, f_hi = cg.frame_range(n_iters=GL_ITERS)
         idx = torch.arange(f_lo, f_hi, device="cuda") % 1000
-        p_l = p_dev[:1000][idx].contiguous()                                   # tiled decoder-shaped power-dB rows
-        ph_l = ph_dev[:1000][idx].contiguous()
+        p_l = p1000[idx].contiguous()                                          # tiled decoder-shaped power-dB rows
+        ph_l = ph1000[idx].contiguous()
 
         def long_step():
             y = cg.from_power_to_wav(p_l, ph_l, n_iter=GL_ITERS, **{k: v for k, v in GL_KW.items()
@@ -571,6 +577,11 @@ def main():
     if not args.no_selfcheck and gl is not None:
         selfcheck = {}
         try:
+            if long_full is None:
+                p1000, ph1000 = p_dev[:1000].clone(), ph_dev[:1000].clone()
+                if world > 1:
+                    dist.broadcast(p1000, src=0)
+                    dist.broadcast(ph1000, src=0)
             # (1) sharded == single, bit for bit
             sw = [synth.utterance(900 + i, s) for i, s in enumerate([1.0, 0.4, 2.0, 0.7, 1.3, 0.2, 0.9, 3.0])]
             got = D.featurize_sharded(sw, gather=True, return_device=True, **hp)
@@ -581,14 +592,14 @@ def main():
             def unchunked(T, n_iter, realse):
                 ii = torch.arange(T, device="cuda") % 1000
                 kw = dict(GL_KW); kw["realse"] = realse
-                return al.from_power_to_wav_batch([p_dev[:1000][ii]], n_iter=n_iter, verbose=False, n_fft=None,
-                                                  phase0s=[ph_dev[:1000][ii].t()], return_device=True, **kw)[0]
+                return al.from_power_to_wav_batch([p1000[ii]], n_iter=n_iter, verbose=False, n_fft=None,
+                                                  phase0s=[ph1000[ii].t()], return_device=True, **kw)[0]
 
             def chunked(T, n_iter, realse, k):
                 c = D.ChunkedGriffinLim(T, 80, 400, steps_per_exchange=k)
                 lo_f, hi_f = c.frame_range(n_iters=n_iter)
                 ii = torch.arange(lo_f, hi_f, device="cuda") % 1000
-                y = c.from_power_to_wav(p_dev[:1000][ii].contiguous(), ph_dev[:1000][ii].contiguous(), P_dB_norm_factor=0.01,
+                y = c.from_power_to_wav(p1000[ii].contiguous(), ph1000[ii].contiguous(), P_dB_norm_factor=0.01,
                                         pre_emphasis=0.97, mean_abs_amp_norm=0.045, n_iter=n_iter, realse=realse)
                 return c.gather(y, dst=None)
             ok2 = bool(torch.equal(chunked(2001, 25, 1.2, 4), unchunked(2001, 25, 1.2)))

@@ -184,84 +184,3 @@ def build_spec_cache(ds: Dict[str, list], cfg_d: dict, path: str, phn_conv_d: Op
                 grp["mel_dB"].create_dataset(str(i), data=mel_db)
                 grp["power_dB"].create_dataset(str(i), data=power_db)
     return used
-
-
-# ----------------------------------------------------------------------------------------------- window samplers
-# the training-side readers of the cache.  Host-side index logic only (random crops of
-# n_timesteps frames); they draw from the global NumPy RNG in exactly the reference's order, so with the same seed and
-# the same cache they yield the same batches as TIMIT_reader.py:474-523 / sound_ds.py:262-350.
-
-def window_sampler(cache, sample_ids, n_timesteps, batch_size=32, n_epochs=1, randomize_samples=True, yield_idxs=False):
-    """``TIMIT.window_sampler`` (TIMIT_reader.py:474-523): batches of (mfcc window, phn window).
-
-    ``sample_ids``: the utterance indices that pass the reader's ``ds_filter`` (``np.arange(n)[f_s]``).  Utterances
-    with ``spec_len <= n_timesteps`` are skipped without consuming random numbers; every kept one draws one
-    ``np.random.randint(0, spec_len - n_timesteps)``; each epoch starts with one ``np.random.shuffle``.
-    """
-    samples_v = [str(int(i)) for i in sample_ids]                 # a Python list, like the reference
-    x_v, y_v, idxs_v = [], [], []
-    for _ in range(n_epochs):
-        if randomize_samples:
-            np.random.shuffle(samples_v)
-        for i_sample in samples_v:
-            mfcc = cache["mfcc"][i_sample]
-            spec_len = mfcc.shape[0]
-            if spec_len <= n_timesteps:
-                continue
-            i_s = np.random.randint(0, spec_len - n_timesteps)
-            i_e = i_s + n_timesteps
-            x_v.append(mfcc[i_s:i_e])
-            y_v.append(cache["phn"][i_sample][i_s:i_e])
-            idxs_v.append([i_s, i_e, int(i_sample)])
-            if len(x_v) == batch_size:
-                x, y = np.array(x_v), np.array(y_v)
-                assert x.shape[1] == y.shape[1] == n_timesteps
-                yield (x, y, np.array(idxs_v)) if yield_idxs else (x, y)
-                x_v, y_v, idxs_v = [], [], []
-
-
-def spec_window_sampler(cache, sample_ids, n_timesteps, batch_size=32, n_epochs=1, randomize_samples=True,
-                        sample_trn=True, prop_val=0.3, random_seed=None, yield_idxs=False, verbose=True):
-    """``Sound_DS.spec_window_sampler`` (sound_ds.py:262-350): batches of (mfcc, mel_dB, power_dB) windows.
-
-    The train / validation split is the reference's: seed 0, shuffle of ``arange``, last ``int(prop_val * n)`` ids are
-    validation, then ``np.random.seed(random_seed)``.  Utterances with ``spec_len <= n_timesteps`` are zero padded (as
-    float64, like ``_zero_pad``'s ``np.zeros``) instead of cropped and consume no random number.
-    """
-    samples_v = np.array([str(int(i)) for i in sample_ids])       # a NumPy array of str, like the reference
-    if prop_val > 0.0:
-        np.random.seed(0)
-        idx_v = np.arange(samples_v.shape[0])
-        np.random.shuffle(idx_v)
-        n_val = int(prop_val * samples_v.shape[0])
-        samples_v = samples_v[idx_v[:-n_val]] if sample_trn else samples_v[idx_v[-n_val:]]
-        np.random.seed(random_seed)
-    names = ("mfcc", "mel_dB", "power_dB")
-    acc = {k: [] for k in names}
-    idxs_v, n_warning = [], 0
-    for _ in range(n_epochs):
-        if randomize_samples:
-            np.random.shuffle(samples_v)
-        for i_sample in samples_v:
-            spec_len = cache["mfcc"][i_sample].shape[0]
-            if spec_len <= n_timesteps:
-                i_s, i_e = 0, n_timesteps
-                pad = n_timesteps - spec_len
-                for k in names:
-                    a = cache[k][i_sample][:]
-                    acc[k].append(np.concatenate([a, np.zeros((pad, a.shape[1]))], axis=0))
-                if verbose and n_warning < 5:
-                    print("WARNING: padding!!!")
-                    n_warning += 1
-            else:
-                i_s = np.random.randint(0, spec_len - n_timesteps)
-                i_e = i_s + n_timesteps
-                for k in names:
-                    acc[k].append(cache[k][i_sample][i_s:i_e])
-            idxs_v.append([i_s, i_e, int(i_sample)])
-            if len(acc["mfcc"]) == batch_size:
-                out = tuple(np.array(acc[k]) for k in names)
-                assert out[0].shape[1] == out[1].shape[1] == out[2].shape[1] == n_timesteps
-                yield out + (np.array(idxs_v),) if yield_idxs else out
-                acc = {k: [] for k in names}
-                idxs_v = []
