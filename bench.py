@@ -326,7 +326,7 @@ def main():
     prof /= n_prof
     kern_ms = float(prof.sum())
     names = ["gain: k_abs_pairwise4 + k_gain_finalize (k_fe_setup only when the layout changes)", "pass A: k_fe_pass_a_ws",
-             "pass B: k_fe_c00 + k_fe_pass_b3"]
+             "pass B: k_fe_pass_b3 (MFCC[0,0] inside)"]
     tkeys = ["gain", "pass_a", "pass_b"]
     top = int(np.argmax(prof))
     fe_bytes = FE_BYTES_PER_FRAME * frames

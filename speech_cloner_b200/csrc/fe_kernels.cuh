@@ -860,9 +860,13 @@ struct B3Tile {
 };
 
 // One (row, coefficient group) DCT task: 4 even + 4 odd coefficients, weights as broadcast 128-bit shared loads.
+// Row kB3Rows of the folded tile carries frame 0 of the UTTERANCE: the lane that owns it in the first coefficient group
+// computes MFCC[0, 0] (audio_lib.py:221) with exactly the multiply-add chain of coefficient 0 of a real row, so that
+// MFCC[0, 0] - MFCC[0, 0] is exactly 0 like the reference's, and the warp picks it up with one shuffle (this replaces
+// the separate k_fe_c00 launch of round 1).
 __device__ __forceinline__ void b3_dct_group(const float4* __restrict__ e4, const float4* __restrict__ o4,
-                                             const float2* __restrict__ x, bool first_group, float c00, float sc,
-                                             float* __restrict__ out) {
+                                             const float2* __restrict__ x, bool first_group, bool norm_first, bool store,
+                                             float sc, float* __restrict__ out) {
     float ae0 = 0.f, ae1 = 0.f, ae2 = 0.f, ae3 = 0.f, ao0 = 0.f, ao1 = 0.f, ao2 = 0.f, ao3 = 0.f;
 #pragma unroll 8
     for (int n = 0; n < kB3Half; ++n) {
@@ -871,10 +875,15 @@ __device__ __forceinline__ void b3_dct_group(const float4* __restrict__ e4, cons
         ae0 = fmaf(e.x, v.x, ae0); ae1 = fmaf(e.y, v.x, ae1); ae2 = fmaf(e.z, v.x, ae2); ae3 = fmaf(e.w, v.x, ae3);
         ao0 = fmaf(o.x, v.y, ao0); ao1 = fmaf(o.y, v.y, ao1); ao2 = fmaf(o.z, v.y, ao2); ao3 = fmaf(o.w, v.y, ao3);
     }
-    if (first_group) ae0 -= c00;
-    float4* __restrict__ c = reinterpret_cast<float4*>(out);
-    c[0] = make_float4(sc * ae0, sc * ao0, sc * ae1, sc * ao1);
-    c[1] = make_float4(sc * ae2, sc * ao2, sc * ae3, sc * ao3);
+    if (first_group) {                                               // warp-uniform: one warp per coefficient group
+        const float c00 = __shfl_sync(0xffffffffu, ae0, kB3Rows);
+        if (norm_first) ae0 -= c00;
+    }
+    if (store) {
+        float4* __restrict__ c = reinterpret_cast<float4*>(out);
+        c[0] = make_float4(sc * ae0, sc * ao0, sc * ae1, sc * ao1);
+        c[1] = make_float4(sc * ae2, sc * ao2, sc * ae3, sc * ao3);
+    }
 }
 
 // Persistent: a CTA keeps the DCT basis in shared memory for its whole life and loads tile i+1 into registers
@@ -896,7 +905,7 @@ k_fe_pass_b3(const B3Tile* __restrict__ tiles, int total_tiles, FeTables tb, FeP
              float* __restrict__ mfcc_out) {
     __shared__ __align__(16) float dct_e[kB3Half * (kB3Mfcc / 2)];   // [n][q/2]
     __shared__ __align__(16) float dct_o[kB3Half * (kB3Mfcc / 2)];
-    __shared__ __align__(16) float2 sd_s[kB3Rows * kB3SdLd];      // (x[n] + x[79-n], x[n] - x[79-n])
+    __shared__ __align__(16) float2 sd_s[(kB3Rows + 1) * kB3SdLd];   // (x[n] + x[79-n], x[n] - x[79-n]); last row: frame 0 of the utterance
     __shared__ __align__(16) float cc_s[kB3Rows * kB3CcLd];       // scaled cepstra
     const int tid = threadIdx.x;
     const float cl = prm.clip ? 1.0f : __int_as_float(0x7f800000);
@@ -906,8 +915,10 @@ k_fe_pass_b3(const B3Tile* __restrict__ tiles, int total_tiles, FeTables tb, FeP
     for (int e = tid; e < kB3Half * (kB3Mfcc / 2); e += kB3Threads) { dct_e[e] = tb.dct_e[e]; dct_o[e] = tb.dct_o[e]; }
 
     float4 pv[kPdbIt], a[kMelIt], b[kMelIt];
+    float c0a = 0.f, c0b = 0.f;            // frame 0 of the utterance, raw mel dB bins tid and 79 - tid (threads 0..39)
     B3Tile tl;
     UttStat st;
+    static_assert(kB3Rows + 1 <= 32, "lane = row, plus the MFCC[0, 0] row");
     // load(): descriptor + every global load of a tile, issued back to back
     auto load = [&](int tile) {
         tl = tiles[tile];
@@ -931,6 +942,11 @@ k_fe_pass_b3(const B3Tile* __restrict__ tiles, int total_tiles, FeTables tb, FeP
                 b[it] = B3_LD(msrc + (int64_t)t * kRow4 + (kRow4 - 1 - m4));
             }
         }
+        if (tid < kB3Half) {
+            const float* __restrict__ row = mel_raw + tl.frame_off * kB3Mels;
+            c0a = B3_LD(row + tid);
+            c0b = B3_LD(row + (kB3Mels - 1 - tid));
+        }
     };
     int tile = blockIdx.x;
     if (tile < total_tiles) load(tile);
@@ -939,7 +955,6 @@ k_fe_pass_b3(const B3Tile* __restrict__ tiles, int total_tiles, FeTables tb, FeP
         const int nfr = min(kB3Frames, T - t0);
         const int64_t row0 = tl.frame_off + t0;
         const int64_t frame_off = tl.frame_off;
-        const float c00 = st.pad[0];
         // ---- mel dB rows t0-1 .. t0+nfr (halo for the delta): clip (:172), normalised rows out (:235, :240), fold
         {
             const float m_hi = 2.0f * db10(fmaxf(__uint_as_float(st.m_max), 1e-5f));
@@ -948,6 +963,8 @@ k_fe_pass_b3(const B3Tile* __restrict__ tiles, int total_tiles, FeTables tb, FeP
             const float sub = prm.shift_m ? m_lo : 0.0f;
             const float mul = prm.shift_m ? prm.m_db_norm_factor : 1.0f;
             float4* __restrict__ dst = reinterpret_cast<float4*>(mel_out + frame_off * kB3Mels);
+            // folded, clipped frame 0 of the utterance (for MFCC[0, 0]): s[n] = x[n] + x[79-n], same operations as below
+            if (tid < kB3Half) sd_s[kB3Rows * kB3SdLd + tid] = make_float2(fmaxf(c0a, m_floor) + fmaxf(c0b, m_floor), 0.f);
 #pragma unroll
             for (int it = 0; it < kMelIt; ++it) {
                 const int task = tid + it * kB3Threads;
@@ -1000,9 +1017,10 @@ k_fe_pass_b3(const B3Tile* __restrict__ tiles, int total_tiles, FeTables tb, FeP
         // ---- DCT-II (:176-179): warp = coefficient group (4 even + 4 odd), lane = row
         {
             const int lane = tid & 31, g = tid >> 5;
-            if (lane < kB3Rows)
-                b3_dct_group(reinterpret_cast<const float4*>(dct_e) + g, reinterpret_cast<const float4*>(dct_o) + g,
-                             sd_s + lane * kB3SdLd, g == 0, c00, prm.mfcc_norm_factor, cc_s + lane * kB3CcLd + 8 * g);
+            const int row = lane <= kB3Rows ? lane : 0;                 // lane kB3Rows: frame 0 of the utterance; lane 31 idles on row 0
+            b3_dct_group(reinterpret_cast<const float4*>(dct_e) + g, reinterpret_cast<const float4*>(dct_o) + g,
+                         sd_s + row * kB3SdLd, g == 0, prm.norm_first != 0, lane < kB3Rows, prm.mfcc_norm_factor,
+                         cc_s + row * kB3CcLd + 8 * g);
         }
         __syncthreads();
         // ---- MFCC (+ delta, :226-228) output, clip (:238)

@@ -308,11 +308,14 @@ k_fe_pass_a_ws(const float* __restrict__ wav, const WsTile* __restrict__ tiles, 
             __syncwarp();
             return gain;
         };
+        // Tiles are walked from the LAST utterance to the first: the |y| pass before this kernel read the batch front to
+        // back, so its tail is what L2 still holds, and pass B (front to back) then starts on the raw tiles this kernel
+        // wrote last - they are re-read from L2 and overwritten in place before they are ever written back to DRAM.
         auto fetch = [&](int n) -> WsTile {
             const int tile = blockIdx.x + n * G;
             WsTile t;
             t.sample_off = 0; t.L = 1; t.frame_row = 0; t.u = 0; t.t0 = 0; t.nfr = 0; t.edge = 0;
-            if (tile < total_tiles) t = tiles[tile];
+            if (tile < total_tiles) t = tiles[total_tiles - 1 - tile];
             return t;
         };
         long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;

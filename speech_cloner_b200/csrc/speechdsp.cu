@@ -643,7 +643,7 @@ static int frontend_run(sc_plan* pl, const float* wav, const int64_t* soff, cons
     // one launch writes every layout table (sub-tree records of the |y| sum, pass A tiles, pass B tiles); skipped when
     // the tables of the previous call are still valid
     if (!hit) {
-        SetupArgs sa;
+        SetupArgs sa{};
         sa.pre_abs = at<int32_t>(dd, fc.o_pabs); sa.pre_ws = at<int32_t>(dd, fc.o_pint); sa.pre_b3 = at<int32_t>(dd, fc.o_pb3);
         sa.heap_off = at<int64_t>(dd, fc.o_heap);
         sa.n_abs = fc.n_abs;
@@ -704,12 +704,13 @@ static int frontend_run(sc_plan* pl, const float* wav, const int64_t* soff, cons
     const bool vec_b = fc.vec_rows && pl->prm.n_mels % 8 == 0 && pl->prm.n_mfcc % 4 == 0 &&
                        ((reinterpret_cast<uintptr_t>(pdb) | reinterpret_cast<uintptr_t>(mel) | reinterpret_cast<uintptr_t>(mfcc)) & 15) == 0;
     if (vec_b) {
-        k_fe_c00<<<(n + 3) / 4, 128, 0, st>>>(rg, tb, fp, stat, mel_raw);
-        SC_LAUNCHED();
         if (b3) {
+            // MFCC[0, 0] is computed inside the kernel (extra row of the folded tile)
             const int grid = fc.n_b3 < 3 * n_sm ? fc.n_b3 : 3 * n_sm;
             k_fe_pass_b3<<<grid, kB3Threads, 0, st>>>(b3_tiles, fc.n_b3, tb, fp, stat, mel_raw, pdb, mel, mfcc);
         } else {
+            k_fe_c00<<<(n + 3) / 4, 128, 0, st>>>(rg, tb, fp, stat, mel_raw);
+            SC_LAUNCHED();
             const size_t smem = fb2_layout(pl->prm.n_mels, pl->prm.n_mfcc).bytes;
             SC_CUDA(cudaFuncSetAttribute(k_fe_pass_b2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_fe_pass_b2<<<fc.n_b, kFbThreads, smem, st>>>(rg, tb, fp, stat, mel_raw, pdb, mel, mfcc, pl->n_bins);
@@ -767,7 +768,7 @@ extern "C" int sc_mean_abs_batch(sc_plan* pl, const float* wav, const int64_t* s
     rg.int_first = nullptr; rg.int_count = nullptr;
     float* heap = reinterpret_cast<float*>(wb + w_heap);
     AbsRec* recs = reinterpret_cast<AbsRec*>(wb + w_rec);
-    SetupArgs sa;
+    SetupArgs sa{};
     sa.pre_abs = at<int32_t>(pl, o_p); sa.pre_ws = nullptr; sa.pre_b3 = nullptr;
     sa.heap_off = at<int64_t>(pl, o_h);
     sa.n_abs = pre[n]; sa.n_ws = 0; sa.n_b3 = 0; sa.ws_frames = kWsFrames;
