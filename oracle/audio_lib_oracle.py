@@ -428,3 +428,30 @@ def normalize_wav(y):
     mag = np.max(np.abs(y)) if y.size else 0.0
     tiny = np.finfo(y.dtype if np.issubdtype(y.dtype, np.floating) else np.float32).tiny
     return y if mag < tiny else y / mag
+
+
+def window_batches(mfcc, mel, stft, cfg_d, t_s=5, t_e=60):
+    """Literal transcription of the batching in conversion2 (test.py:92-128): returns what is fed to decoder.predict."""
+    hop = cfg_d['hop_length']
+    n_times = cfg_d['n_timesteps']
+    if mfcc.shape[0] % n_times != 0:
+        pad_len = (n_times) - (mfcc.shape[0] % n_times)
+        pad_mfcc = np.zeros((pad_len, mfcc.shape[1]))
+        mfcc = np.concatenate([mfcc, pad_mfcc], axis=0)
+        pad_mel = np.zeros((pad_len, mel.shape[1]))
+        mel = np.concatenate([mel, pad_mel], axis=0)
+        pad_stft = np.zeros((pad_len, stft.shape[1]))
+        stft = np.concatenate([stft, pad_stft], axis=0)
+    n_hop_s = t_s * cfg_d['sample_rate'] // hop
+    n_hop_e = t_e * cfg_d['sample_rate'] // hop
+    n_hop_e = min(n_hop_e, mfcc.shape[0])
+    n_delta = n_times * ((n_hop_e - n_hop_s) // n_times)
+    n_s = n_hop_s
+    n_e = n_hop_s + n_delta
+    if n_e <= n_s:
+        raise Exception(' - ERROR, translate: n_e <= n_s.')
+    mfcc_input0 = mfcc[n_s:n_e].reshape((-1, n_times, mfcc.shape[-1]))
+    mfcc_input1 = None
+    if n_e - n_s > n_times:
+        mfcc_input1 = mfcc[(n_s + n_times // 2):(n_e - n_times // 2)].reshape((-1, n_times, mfcc.shape[-1]))
+    return mfcc_input0, mfcc_input1, mel[n_s:n_e], stft[n_s:n_e], n_s, n_e
