@@ -30,7 +30,6 @@ CPU oracle with all host cores on the same config (rank 0 only) and prints the s
 from __future__ import annotations
 
 import argparse
-import hashlib
 import json
 import multiprocessing as mp
 import os
@@ -84,14 +83,8 @@ def hbm_peak():
 
 def kernel_source_hash() -> str:
     """sha256 over the kernel sources and the header: pins profiles/r02_traffic.json to the code it was captured from."""
-    h = hashlib.sha256()
-    base = os.path.join(ROOT, "speech_cloner_b200", "csrc")
-    for name in sorted(os.listdir(base)):
-        if name.endswith((".cu", ".cuh")):
-            h.update(name.encode())
-            h.update(open(os.path.join(base, name), "rb").read())
-    h.update(open(os.path.join(ROOT, "include", "speechdsp.h"), "rb").read())
-    return h.hexdigest()
+    from speech_cloner_b200 import build
+    return build.source_hash()
 
 
 def load_traffic():
@@ -506,7 +499,7 @@ def main():
         if world > 1:
             dist.broadcast(p1000, src=0)
             dist.broadcast(ph1000, src=0)
-        cg = D.ChunkedGriffinLim(T_LONG, 80, 400, steps_per_exchange=20)
+        cg = D.ChunkedGriffinLim(T_LONG, 80, 400, steps_per_exchange=40)
         f_lo, f_hi = cg.frame_range(n_iters=GL_ITERS)
         idx = torch.arange(f_lo, f_hi, device="cuda") % 1000
         p_l = p1000[idx].contiguous()                                          # tiled decoder-shaped power-dB rows

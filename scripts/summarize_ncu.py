@@ -86,16 +86,19 @@ def full(src, dst):
 
 
 GROUPS = [   # bench.py roofline groups -> kernels of one front-end step
-    ("gain: k_fe_setup + k_abs_pairwise4 + k_gain_finalize", ("k_fe_setup", "k_abs_pairwise", "k_gain_finalize")),
-    ("pass A: k_fe_pass_a_ws", ("k_fe_pass_a",)),
-    ("pass B: k_fe_c00 + k_fe_pass_b3", ("k_fe_c00", "k_fe_pass_b", "k_b3_tiles")),
-    ("k_gl_iter_persist", ("k_gl_iter_persist",)),
+    ("gain", ("k_fe_setup", "k_abs_pairwise", "k_gain_finalize")),
+    ("pass_a", ("k_fe_pass_a",)),
+    ("pass_b", ("k_fe_c00", "k_fe_pass_b")),
+    ("gl_iter", ("k_gl_iter_persist",)),
 ]
 
 
 def traffic(src, dst):
-    """DRAM read + write bytes per launch (last = warm launch of every kernel), summed per bench group."""
+    """DRAM read + write bytes per launch (last = warm launch of every kernel), summed per bench group, and pinned to
+    the kernel sources they were captured from (bench.py reports them only while the hash still matches)."""
     import json
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
@@ -104,11 +107,14 @@ def traffic(src, dst):
     seen = collections.OrderedDict()
     for r in rows[2:]:
         seen[r[ki].split("(")[0].split("::")[-1]] = float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]]
+    from speech_cloner_b200 import build
+    sha = build.source_hash()
     res = {"_source": f"{src}: dram__bytes_read.sum + dram__bytes_write.sum per launch (last launch of each kernel), "
                       "ncu --set full, config-2 front-end shape (256 x 4 s) and config-3 Griffin-Lim shape",
+           "_src_sha256": sha,
            "_kernels": seen}
     for name, pats in GROUPS:
-        res[name] = sum(v for k, v in seen.items() if any(k.startswith(p_) or ("<" in k and k.split("<")[0].endswith(p_)) or p_ in k for p_ in pats))
+        res[name] = sum(v for k, v in seen.items() if any(p_ in k for p_ in pats))
     with open(dst, "w") as f:
         json.dump(res, f, indent=1)
 

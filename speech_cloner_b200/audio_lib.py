@@ -621,29 +621,11 @@ def _stage_rows(items, layout, n_bins, torch, transpose_from_freq_major: bool, l
     return dst
 
 
-def from_power_to_wav_batch(Ps, P_dB_norm_factor=0.01, pre_emphasis=0.97, hop_length=40, win_length=800,
-                            mean_abs_amp_norm=0.01, n_iter=200, n_fft=None, realse=1.0, verbose=False,
-                            phase0s=None, return_device=False):
-    """``from_power_to_wav`` over a list of (T, bins) spectrograms as one ragged GPU batch.
-
-    ``phase0s`` is a list of (bins, T) initial phases (reference orientation) or ``None`` (drawn per utterance from the
-    global NumPy state in list order, like calling the reference in a loop).
-    """
-    if int(n_iter) < 1:
-        raise ValueError("n_iter must be >= 1 (the reference's griffin_lim_alg returns None for 0 iterations)")
-    torch = _require_cuda()
-    lib = _lib.load()
-    plan = _gl_plan(win_length, hop_length, n_fft)
-    Ps = list(Ps)
-    for P in Ps:
-        if len(P.shape) != 2 or P.shape[1] != plan.n_bins:
-            raise ValueError("P must have shape (T, 1 + n_fft//2)")
-        if P.shape[0] < 2:
-            raise ValueError("P needs at least 2 frames")
+def _power_to_wav_device(plan, lib, torch, Ps, phase0s, P_dB_norm_factor, pre_emphasis, mean_abs_amp_norm, n_iter, realse, verbose):
+    """Stage, convert, invert and de-emphasise one group of spectrograms; everything is queued on the current stream.
+    Returns (packed float64 device waveforms, layout)."""
     layout = _GlLayout([P.shape[0] for P in Ps], plan.hop_length)
     n = len(Ps)
-    if phase0s is None:
-        phase0s = [np.pi * np.random.rand(plan.n_bins, P.shape[0]) for P in Ps]      # :255
     p_dev = _stage_rows(Ps, layout, plan.n_bins, torch, False, lib)
     ph_dev = _stage_rows(list(phase0s), layout, plan.n_bins, torch, True, lib)
     st = _stream_ptr(torch)
@@ -658,10 +640,52 @@ def from_power_to_wav_batch(Ps, P_dB_norm_factor=0.01, pre_emphasis=0.97, hop_le
     _lib.check(lib.sc_deemph_renorm_batch(plan._h, wav.data_ptr(), layout.c_sample_offsets, layout.c_sample_lengths,
                                           n, float(pre_emphasis), float(mean_abs_amp_norm), out.data_ptr(), st),
                "sc_deemph_renorm_batch")
+    return out, layout
+
+
+def from_power_to_wav_batch(Ps, P_dB_norm_factor=0.01, pre_emphasis=0.97, hop_length=40, win_length=800,
+                            mean_abs_amp_norm=0.01, n_iter=200, n_fft=None, realse=1.0, verbose=False,
+                            phase0s=None, return_device=False, pipeline_groups=4):
+    """``from_power_to_wav`` over a list of (T, bins) spectrograms as one ragged GPU batch.
+
+    ``phase0s`` is a list of (bins, T) initial phases (reference orientation) or ``None`` (drawn per utterance from the
+    global NumPy state in list order, like calling the reference in a loop).  Host inputs are processed in
+    ``pipeline_groups`` groups queued back to back on the current stream: while the GPU inverts group g the host packs
+    group g+1 into pinned memory, so the staging cost is hidden behind the 200 iterations (utterances are independent:
+    the results do not depend on the grouping).
+    """
+    if int(n_iter) < 1:
+        raise ValueError("n_iter must be >= 1 (the reference's griffin_lim_alg returns None for 0 iterations)")
+    torch = _require_cuda()
+    lib = _lib.load()
+    plan = _gl_plan(win_length, hop_length, n_fft)
+    Ps = list(Ps)
+    for P in Ps:
+        if len(P.shape) != 2 or P.shape[1] != plan.n_bins:
+            raise ValueError("P must have shape (T, 1 + n_fft//2)")
+        if P.shape[0] < 2:
+            raise ValueError("P needs at least 2 frames")
+    n = len(Ps)
+    if phase0s is None:
+        phase0s = [np.pi * np.random.rand(plan.n_bins, P.shape[0]) for P in Ps]      # :255
+    phase0s = list(phase0s)
+    on_host = not all(_is_tensor(x) for x in Ps + phase0s)
+    # groups of at least 8 spectrograms (a group should still fill the GPU: ~300 tiles of 28 hops)
+    g = max(1, min(int(pipeline_groups), n // 8)) if (on_host and not verbose) else 1
+    step = -(-n // g)
+    bounds = [(i, min(n, i + step)) for i in range(0, n, step)]
+    kw = dict(P_dB_norm_factor=P_dB_norm_factor, pre_emphasis=pre_emphasis, mean_abs_amp_norm=mean_abs_amp_norm,
+              n_iter=n_iter, realse=realse, verbose=verbose)
+    parts = [_power_to_wav_device(plan, lib, torch, Ps[a:b], phase0s[a:b], **kw) for a, b in bounds]
+    outs = []
     if return_device:
-        return [out[o:o + m] for o, m in zip(layout.sample_offsets, layout.samples)]
-    host, = _to_host(torch, out)
-    return [host[o:o + m] for o, m in zip(layout.sample_offsets, layout.samples)]
+        for out, layout in parts:
+            outs += [out[o:o + m] for o, m in zip(layout.sample_offsets, layout.samples)]
+        return outs
+    hosts = _to_host(torch, *[out for out, _ in parts])
+    for host, (_, layout) in zip(hosts, parts):
+        outs += [host[o:o + m] for o, m in zip(layout.sample_offsets, layout.samples)]
+    return outs
 
 
 def from_power_to_wav(P,

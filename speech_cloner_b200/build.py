@@ -21,6 +21,20 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 
+def source_hash() -> str:
+    """sha256 over the kernel sources and the C header: pins committed ncu numbers (profiles/*_traffic.json) to the code
+    they were captured from."""
+    import hashlib
+    h = hashlib.sha256()
+    base = os.path.join(_HERE, "csrc")
+    for name in sorted(os.listdir(base)):
+        if name.endswith((".cu", ".cuh")):
+            h.update(name.encode())
+            h.update(open(os.path.join(base, name), "rb").read())
+    h.update(open(os.path.join(_HERE, "..", "include", "speechdsp.h"), "rb").read())
+    return h.hexdigest()
+
+
 def nvcc_path() -> str:
     for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
