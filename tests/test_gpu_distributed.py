@@ -87,3 +87,23 @@ def test_featurize_sharded_nccl():
 def test_chunked_griffin_lim_nccl_bit_identical():
     _need2()
     torch.multiprocessing.spawn(_entry, args=(2, _free_port(), _chunked), nprocs=2, join=True)
+
+
+def test_plan_belongs_to_its_device():
+    """a plan's tables, function attributes and SM count belong to the device it was created on; using it with
+    another device current is refused (SC_ERR_INVALID -> ValueError), and the public API builds one plan per device."""
+    _need2()
+    from speech_cloner_b200 import audio_lib as al
+    y = synth.utterance(11, 1.0)
+    with torch.cuda.device(0):
+        want = al.calc_MFCC_input(y, **HP)
+        plan0 = al.DspPlan(sr=16000, n_fft=400, win_length=400, hop_length=80, n_mels=80, n_mfcc=40)
+    with torch.cuda.device(1):
+        got = al.calc_MFCC_input(y, **HP)                      # second device: its own plan, same results
+        for a, b in zip(got, want):
+            np.testing.assert_array_equal(a, b)
+        lay = al.FrontendLayout([len(y)], 80)
+        dev = torch.from_numpy(y).cuda()
+        with pytest.raises(ValueError):
+            al.frontend_device(plan0, dev, lay)
+    torch.cuda.synchronize(0); torch.cuda.synchronize(1)
