@@ -126,6 +126,21 @@ int sc_phn_target_batch(sc_plan* plan, const int32_t* phn_start_dev, const int32
                         int32_t hop_length, int32_t win_length, int32_t* out_index_dev,
                         const int64_t* frame_offsets_host, void* stream);
 
+/* Window samplers on a feature cache resident in device memory:
+ * Sound_DS.spec_window_sampler (sound_ds.py:262-350) and TIMIT.window_sampler (TIMIT_reader.py:474-523) slice
+ * `ds_h5py[group][i_sample][i_s:i_e]` out of every feature group and zero-pad short utterances
+ * (sound_ds.py:246-259).  The random draws stay with the caller (NumPy's global generator, reference order);
+ * this call copies the windows of one batch out of up to 4 packed buffers in one launch.
+ *   src_dev_ptrs_host[a]   packed [n_rows_total][width[a]] buffer of 32-bit elements (float32 / int32), device
+ *   dst_dev_ptrs_host[a]   dense [n_windows][n_timesteps][width[a]] output, device
+ *   first_row_dev[w]       packed row of the first frame of window w (frame offset of the utterance + i_s)
+ *   valid_rows_dev[w]      rows copied; rows valid_rows..n_timesteps-1 of the window are zero (padding);
+ *                          windows reaching outside [0, n_rows_total) are cut, never read out of bounds */
+int sc_window_gather(const void* const* src_dev_ptrs_host, void* const* dst_dev_ptrs_host,
+                     const int64_t* width_host, int32_t n_arrays, int64_t n_rows_total,
+                     const int64_t* first_row_dev, const int32_t* valid_rows_dev, int32_t n_windows,
+                     int32_t n_timesteps, void* stream);
+
 /* calc_preemphasis / calc_inv_preemphasis (audio_lib.py:12-28, :31-47): float32 in, float64 out
  * (scipy.signal.lfilter promotes), zero initial state, one signal of n samples. */
 int sc_preemphasis(const float* wav_dev, int64_t n, double coeff, double* out_dev, void* stream);

@@ -455,3 +455,72 @@ def window_batches(mfcc, mel, stft, cfg_d, t_s=5, t_e=60):
     if n_e - n_s > n_times:
         mfcc_input1 = mfcc[(n_s + n_times // 2):(n_e - n_times // 2)].reshape((-1, n_times, mfcc.shape[-1]))
     return mfcc_input0, mfcc_input1, mel[n_s:n_e], stft[n_s:n_e], n_s, n_e
+
+
+def _zero_pad(*specs, pad_len=0):
+    """Sound_DS._zero_pad (sound_ds.py:246-259): rows of float64 zeros appended (np.zeros, so the result is float64)."""
+    return [np.concatenate([spec, np.zeros((pad_len, spec.shape[1]))], axis=0) for spec in specs]
+
+
+def spec_window_sampler(cache, sample_ids, n_timesteps, batch_size=32, n_epochs=1, randomize_samples=True,
+                        sample_trn=True, prop_val=0.3, random_seed=None, yield_idxs=False):
+    """Literal transcription of Sound_DS.spec_window_sampler (sound_ds.py:262-350) over an open cache
+    (``cache[group][str(i)]``); ``sample_ids`` stands for ``np.arange(f_s.shape[0])[f_s]`` of the reader's filter and
+    ``random_seed`` for ``self.random_seed``.  Draws from NumPy's global generator exactly like the reference."""
+    samples_v = np.array([str(i) for i in sample_ids])
+    if prop_val > 0.0:
+        np.random.seed(0)                                                  # :270
+        idx_v = np.arange(samples_v.shape[0])
+        np.random.shuffle(idx_v)
+        n_val = int(prop_val * samples_v.shape[0])
+        idx_trn = idx_v[:-n_val]
+        idx_val = idx_v[-n_val:]
+        samples_v = samples_v[idx_trn] if sample_trn else samples_v[idx_val]
+        np.random.seed(random_seed)                                        # :284
+    mfcc_v, mel_dB_v, power_dB_v, idxs_v = [], [], [], []
+    for i_epoch in range(n_epochs):
+        if randomize_samples:
+            np.random.shuffle(samples_v)                                   # :296
+        for i_sample in samples_v:
+            spec_len = cache['mfcc'][i_sample].shape[0]
+            if spec_len <= n_timesteps:                                    # :301-311
+                i_s, i_e = 0, n_timesteps
+                mfcc, mel_dB, power_dB = _zero_pad(cache['mfcc'][i_sample][:], cache['mel_dB'][i_sample][:],
+                                                   cache['power_dB'][i_sample][:], pad_len=n_timesteps - spec_len)
+            else:                                                          # :317-324
+                i_s = np.random.randint(0, spec_len - n_timesteps)
+                i_e = i_s + n_timesteps
+                mfcc = cache['mfcc'][i_sample][i_s:i_e]
+                mel_dB = cache['mel_dB'][i_sample][i_s:i_e]
+                power_dB = cache['power_dB'][i_sample][i_s:i_e]
+            mfcc_v.append(mfcc); mel_dB_v.append(mel_dB); power_dB_v.append(power_dB)
+            idxs_v.append([i_s, i_e, int(i_sample)])
+            if len(mfcc_v) == batch_size:                                  # :334-350
+                out = (np.array(mfcc_v), np.array(mel_dB_v), np.array(power_dB_v))
+                assert out[0].shape[1] == out[1].shape[1] == out[2].shape[1] == n_timesteps
+                yield out + (np.array(idxs_v),) if yield_idxs else out
+                mfcc_v, mel_dB_v, power_dB_v, idxs_v = [], [], [], []
+
+
+def window_sampler(cache, sample_ids, n_timesteps, batch_size=32, n_epochs=1, randomize_samples=True, yield_idxs=False):
+    """Literal transcription of TIMIT.window_sampler (TIMIT_reader.py:474-523): (mfcc window, phn window) batches;
+    utterances with ``spec_len <= n_timesteps`` are skipped without drawing a random number."""
+    samples_v = [str(i) for i in sample_ids]                               # a list here (:478), an array above
+    x_v, y_v, idxs_v = [], [], []
+    for i_epoch in range(n_epochs):
+        if randomize_samples:
+            np.random.shuffle(samples_v)                                   # :489
+        for i_sample in samples_v:
+            spec_len = cache['mfcc'][i_sample].shape[0]
+            if spec_len <= n_timesteps:                                    # :496-497
+                continue
+            i_s = np.random.randint(0, spec_len - n_timesteps)             # :501
+            i_e = i_s + n_timesteps
+            x_v.append(cache['mfcc'][i_sample][i_s:i_e])
+            y_v.append(cache['phn'][i_sample][i_s:i_e])
+            idxs_v.append([i_s, i_e, int(i_sample)])
+            if len(x_v) == batch_size:                                     # :511-523
+                x, y = np.array(x_v), np.array(y_v)
+                assert x.shape[1] == y.shape[1] == n_timesteps
+                yield (x, y, np.array(idxs_v)) if yield_idxs else (x, y)
+                x_v, y_v, idxs_v = [], [], []

@@ -52,6 +52,8 @@ PROTOTYPES = {
     "sc_frontend_batch": (C.c_int, [_P, _P, _I64P, _I64P, C.c_int32, _P, _P, _P, _I64P, _P]),
     "sc_mean_abs_batch": (C.c_int, [_P, _P, _I64P, _I64P, C.c_int32, _P, _P]),
     "sc_phn_target_batch": (C.c_int, [_P, _P, _P, _I64P, _I64P, C.c_int32, C.c_int32, C.c_int32, _P, _I64P, _P]),
+    "sc_window_gather": (C.c_int, [C.POINTER(_P), C.POINTER(_P), _I64P, C.c_int32, C.c_int64, _P, _P, C.c_int32,
+                                   C.c_int32, _P]),
     "sc_preemphasis": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P]),
     "sc_inv_preemphasis": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P]),
     "sc_preemphasis_f64": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P]),

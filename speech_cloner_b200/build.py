@@ -15,7 +15,7 @@ SRC = os.path.join(_HERE, "csrc", "speechdsp.cu")
 OUT = os.path.join(_HERE, "libspeechdsp.so")
 DEPS = [os.path.join(_HERE, "csrc", f) for f in
         ("speechdsp.cu", "common.cuh", "dft20.cuh", "fft400.cuh", "fe_kernels.cuh", "gl_kernels.cuh",
-         "generic_kernels.cuh", "fe_ws.cuh", "phn_kernels.cuh")] + [os.path.join(_HERE, "..", "include", "speechdsp.h")]
+         "generic_kernels.cuh", "fe_ws.cuh", "phn_kernels.cuh", "sampler_kernels.cuh")] + [os.path.join(_HERE, "..", "include", "speechdsp.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

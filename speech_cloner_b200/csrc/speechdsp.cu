@@ -17,6 +17,7 @@
 #include "gl_kernels.cuh"
 #include "generic_kernels.cuh"
 #include "phn_kernels.cuh"
+#include "sampler_kernels.cuh"
 
 using namespace scdsp;
 
@@ -814,6 +815,36 @@ extern "C" int sc_phn_target_batch(sc_plan* pl, const int32_t* phn_start, const 
     for (int u0 = 0; u0 < n; u0 += 32768) {
         const int ny = n - u0 < 32768 ? n - u0 : 32768;
         k_phn_target<<<dim3((unsigned)((max_t + 255) / 256), (unsigned)ny), 256, 0, st>>>(pb, u0, out_index);
+        SC_LAUNCHED();
+    }
+    return SC_OK;
+}
+
+// --------------------------------------------------------------------------- window samplers
+extern "C" int sc_window_gather(const void* const* src, void* const* dst, const int64_t* width, int32_t n_arrays,
+                                int64_t n_rows_total, const int64_t* first_row, const int32_t* valid, int32_t n_windows,
+                                int32_t n_timesteps, void* stream) {
+    if (!src || !dst || !width || !first_row || !valid) return fail(SC_ERR_INVALID, "sc_window_gather: null argument");
+    if (n_arrays < 1 || n_arrays > kGatherMaxArrays)
+        return fail(SC_ERR_INVALID, "sc_window_gather: between 1 and 4 arrays per call");
+    if (n_windows < 0 || n_timesteps < 1 || n_rows_total < 0) return fail(SC_ERR_INVALID, "sc_window_gather: bad size");
+    GatherArgs g{};
+    int64_t max_words = 0;
+    for (int a = 0; a < n_arrays; ++a) {
+        if (!src[a] || !dst[a] || width[a] < 1) return fail(SC_ERR_INVALID, "sc_window_gather: null array or width < 1");
+        if ((reinterpret_cast<uintptr_t>(src[a]) | reinterpret_cast<uintptr_t>(dst[a])) & 3)
+            return fail(SC_ERR_INVALID, "sc_window_gather: arrays must be 4-byte aligned");
+        g.a[a].src = static_cast<const uint32_t*>(src[a]);
+        g.a[a].dst = static_cast<uint32_t*>(dst[a]);
+        g.a[a].width = width[a];
+        max_words = std::max(max_words, width[a] * (int64_t)n_timesteps);
+    }
+    if (n_windows == 0) return SC_OK;
+    const int64_t bx = std::min<int64_t>((max_words + kGatherWordsPerBlock - 1) / kGatherWordsPerBlock, 1024);
+    for (int32_t w0 = 0; w0 < n_windows; w0 += 32768) {
+        const int ny = n_windows - w0 < 32768 ? n_windows - w0 : 32768;
+        k_window_gather<<<dim3((unsigned)bx, (unsigned)ny, (unsigned)n_arrays), kGatherThreads, 0, (cudaStream_t)stream>>>(
+            g, first_row, valid, w0, n_timesteps, n_rows_total);
         SC_LAUNCHED();
     }
     return SC_OK;

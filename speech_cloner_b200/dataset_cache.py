@@ -14,6 +14,10 @@ Here the same loop runs in batches through ``sc_frontend_batch`` / ``sc_phn_targ
 layout.  ``h5py`` is used when importable (files are then readable by the unchanged reference samplers,
 sound_ds.py:262-350); otherwise an ``.npz`` with keys ``"<group>/<i_sample>"`` holds the same arrays
 (:func:`open_cache` reads both).  Nothing here computes features on the CPU.
+
+The training-side readers of the cache are here too: :class:`DeviceSpecCache` keeps a cache
+resident in device memory and :func:`spec_window_sampler` / :func:`window_sampler` cut the reference's random windows
+out of it with one ``sc_window_gather`` launch per batch (sound_ds.py:262-350, TIMIT_reader.py:474-523).
 """
 from __future__ import annotations
 
@@ -24,6 +28,7 @@ from typing import Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
 
+from . import _lib
 from . import audio_lib as al
 
 # DSP keys hashed into the cache name, in the reference's order
@@ -184,3 +189,191 @@ def build_spec_cache(ds: Dict[str, list], cfg_d: dict, path: str, phn_conv_d: Op
                 grp["mel_dB"].create_dataset(str(i), data=mel_db)
                 grp["power_dB"].create_dataset(str(i), data=power_db)
     return used
+
+
+# ----------------------------------------------------------------------------------------------- window samplers
+# SURVEY.md §8(f) rank 4.  The reference's samplers re-open the HDF5 cache and slice one window per utterance on the host
+# (`ds_h5py['mfcc'][i_sample][i_s:i_e]`, one h5py read per group and window).  Here the cache stays in HBM (10 h of audio
+# are 10.4 GB of features) and a batch is ONE kernel launch; only the random numbers stay on the host, drawn from NumPy's
+# global generator in exactly the reference's order, so the same seed gives the same windows.
+
+class DeviceSpecCache:
+    """A feature cache resident in device memory: packed ``[rows][width]`` CUDA tensors per group.
+
+    ``groups``        ``{"mfcc": …, "mel_dB": …, "power_dB": …[, "phn": …]}`` (float32; ``phn`` int32, ``[rows]`` or
+                      ``[rows][k]`` for one-hot targets), all sharing one row layout
+    ``frame_offsets`` first row of every utterance, ``spec_len`` its number of frames
+    ``keys``          the cache key (``str(i_sample)``) of every slot
+    """
+
+    FEATURES = ("mfcc", "mel_dB", "power_dB")
+
+    def __init__(self, groups, frame_offsets, spec_len, keys=None):
+        torch = al._require_cuda()
+        self.groups = {}
+        rows = None
+        for name, t in groups.items():
+            if not (al._is_tensor(t) and t.is_cuda and t.is_contiguous() and t.element_size() == 4):
+                raise ValueError(f"{name}: contiguous CUDA tensor of 32-bit elements expected")
+            if rows is None:
+                rows = t.shape[0]
+            elif t.shape[0] != rows:
+                raise ValueError("all groups must share the row layout")
+            self.groups[name] = t
+        self.n_rows = int(rows)
+        self.frame_offsets = np.asarray(frame_offsets, dtype=np.int64)
+        self.spec_len = np.asarray(spec_len, dtype=np.int64)
+        if self.frame_offsets.shape != self.spec_len.shape:
+            raise ValueError("frame_offsets and spec_len differ in length")
+        if len(self.spec_len) and int((self.frame_offsets + self.spec_len).max()) > self.n_rows:
+            raise ValueError("an utterance reaches beyond the packed buffers")
+        keys = [str(i) for i in range(len(self.spec_len))] if keys is None else [str(k) for k in keys]
+        self.slot = {k: i for i, k in enumerate(keys)}
+        self._torch = torch
+
+    # -- constructors
+    @classmethod
+    def from_device(cls, mfcc, mel_dB, power_dB, layout, phn=None, keys=None):
+        """Wrap the packed outputs of :func:`audio_lib.frontend_device` (no copy): a cache that never left the GPU."""
+        groups = {"mfcc": mfcc, "mel_dB": mel_dB, "power_dB": power_dB}
+        if phn is not None:
+            groups["phn"] = phn
+        return cls(groups, layout.frame_offsets[:-1], layout.frames, keys)
+
+    @classmethod
+    def from_arrays(cls, arrays: Dict[str, Sequence[np.ndarray]], keys=None):
+        """Upload per-utterance host arrays (``arrays[group][u]`` of shape ``[T_u, width]`` or ``[T_u]``)."""
+        torch = al._require_cuda()
+        names = list(arrays)
+        lens = [int(np.shape(a)[0]) for a in arrays[names[0]]]
+        off = np.zeros(len(lens) + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        groups = {}
+        for name in names:
+            seq = arrays[name]
+            if [int(np.shape(a)[0]) for a in seq] != lens:
+                raise ValueError(f"{name}: frame counts differ from {names[0]}")
+            first = np.asarray(seq[0])
+            dt = np.int32 if np.issubdtype(first.dtype, np.integer) else np.float32
+            host = torch.empty((int(off[-1]),) + first.shape[1:], dtype=torch.int32 if dt is np.int32 else torch.float32,
+                               pin_memory=True)
+            view = host.numpy()
+            for u, a in enumerate(seq):
+                view[off[u]:off[u + 1]] = np.asarray(a)
+            groups[name] = host.to("cuda", non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return cls(groups, off[:-1], lens, keys)
+
+    @classmethod
+    def from_cache(cls, cache, sample_ids=None, groups=None):
+        """Load an open cache (:func:`open_cache` / h5py): all utterances, or the ones in ``sample_ids``."""
+        if sample_ids is None:
+            sample_ids = sorted((int(k) for k in cache["mfcc"].keys()))
+        keys = [str(int(i)) for i in sample_ids]
+        if groups is None:
+            groups = [g for g in cls.FEATURES + ("phn",) if _has_group(cache, g)]
+        return cls.from_arrays({g: [cache[g][k][...] for k in keys] for g in groups}, keys)
+
+    # -- one batch
+    def gather(self, names, first_rows, valid_rows, n_timesteps):
+        """Windows ``[first_rows[w], +valid_rows[w])`` of the packed rows, zero padded to ``n_timesteps`` rows, from every
+        group in ``names``: dense ``[n_windows, n_timesteps(, width)]`` CUDA tensors out of one launch."""
+        torch = self._torch
+        lib = _lib.load()
+        n_w = len(first_rows)
+        stage = torch.empty(3 * n_w, dtype=torch.int32, pin_memory=True)     # int64 first rows + int32 valid counts
+        host = stage.numpy()
+        host[:2 * n_w].view(np.int64)[:] = np.asarray(first_rows, dtype=np.int64)
+        host[2 * n_w:] = np.asarray(valid_rows, dtype=np.int32)
+        dev = stage.to("cuda", non_blocking=True)
+        outs, srcs, dsts, widths = [], [], [], []
+        for name in names:
+            t = self.groups[name]
+            out = torch.empty((n_w, int(n_timesteps)) + tuple(t.shape[1:]), dtype=t.dtype, device="cuda")
+            outs.append(out)
+            srcs.append(t.data_ptr()); dsts.append(out.data_ptr()); widths.append(int(np.prod(t.shape[1:], dtype=np.int64)))
+        for a0 in range(0, len(names), 4):
+            k = len(names[a0:a0 + 4])
+            rc = lib.sc_window_gather((_lib.C.c_void_p * k)(*srcs[a0:a0 + k]), (_lib.C.c_void_p * k)(*dsts[a0:a0 + k]),
+                                      _lib.i64_array(widths[a0:a0 + k]), k, self.n_rows, dev.data_ptr(),
+                                      dev.data_ptr() + 8 * n_w, n_w, int(n_timesteps), al._stream_ptr(torch))
+            _lib.check(rc, "sc_window_gather")
+        return outs
+
+
+def _has_group(cache, name) -> bool:
+    try:
+        cache[name]
+        return len(cache[name]) > 0
+    except KeyError:
+        return False
+
+
+def spec_window_sampler(cache: DeviceSpecCache, sample_ids, n_timesteps, batch_size=32, n_epochs=1,
+                        randomize_samples=True, sample_trn=True, prop_val=0.3, random_seed=None, yield_idxs=False,
+                        verbose=True):
+    """``Sound_DS.spec_window_sampler`` (sound_ds.py:262-350) on a device-resident cache.
+
+    Yields ``(mfcc_v, mel_dB_v, power_dB_v[, idxs_v])``: float32 CUDA tensors ``[batch_size, n_timesteps, width]`` and
+    the reference's ``[i_s, i_e, i_sample]`` rows as a NumPy array.  ``sample_ids`` is what the reader's filter selects
+    (``np.arange(n)[f_s]``), ``random_seed`` the reader's ``self.random_seed``.  Same random stream as the reference: the
+    seed-0 train / validation split, ``np.random.seed(random_seed)``, one ``np.random.shuffle`` per epoch, one
+    ``np.random.randint(0, spec_len - n_timesteps)`` per utterance longer than the window; shorter ones are zero padded
+    without a draw.  (The reference's padded windows are float64 because of ``np.zeros``; the values are the same.)
+    """
+    samples_v = np.array([str(int(i)) for i in sample_ids])       # a NumPy array of str, like the reference
+    if prop_val > 0.0:
+        np.random.seed(0)
+        idx_v = np.arange(samples_v.shape[0])
+        np.random.shuffle(idx_v)
+        n_val = int(prop_val * samples_v.shape[0])
+        samples_v = samples_v[idx_v[:-n_val]] if sample_trn else samples_v[idx_v[-n_val:]]
+        np.random.seed(random_seed)
+    rows, valid, idxs_v, n_warning = [], [], [], 0
+    for _ in range(n_epochs):
+        if randomize_samples:
+            np.random.shuffle(samples_v)
+        for i_sample in samples_v:
+            u = cache.slot[str(i_sample)]
+            spec_len = int(cache.spec_len[u])
+            if spec_len <= n_timesteps:
+                i_s, i_e = 0, n_timesteps
+                valid.append(spec_len)
+                if verbose and n_warning < 5:
+                    print("WARNING: padding!!!")
+                    n_warning += 1
+            else:
+                i_s = np.random.randint(0, spec_len - n_timesteps)
+                i_e = i_s + n_timesteps
+                valid.append(n_timesteps)
+            rows.append(int(cache.frame_offsets[u]) + i_s)
+            idxs_v.append([i_s, i_e, int(i_sample)])
+            if len(rows) == batch_size:
+                out = tuple(cache.gather(DeviceSpecCache.FEATURES, rows, valid, n_timesteps))
+                yield out + (np.array(idxs_v),) if yield_idxs else out
+                rows, valid, idxs_v = [], [], []
+
+
+def window_sampler(cache: DeviceSpecCache, sample_ids, n_timesteps, batch_size=32, n_epochs=1, randomize_samples=True,
+                   yield_idxs=False):
+    """``TIMIT.window_sampler`` (TIMIT_reader.py:474-523) on a device-resident cache: ``(x_v, y_v[, idxs_v])`` with the
+    mfcc windows ``[batch_size, n_timesteps, width]`` and the phoneme targets ``[batch_size, n_timesteps(, k)]`` as CUDA
+    tensors.  Utterances with ``spec_len <= n_timesteps`` are skipped without consuming a random number."""
+    samples_v = [str(int(i)) for i in sample_ids]                 # a Python list, like the reference
+    rows, valid, idxs_v = [], [], []
+    for _ in range(n_epochs):
+        if randomize_samples:
+            np.random.shuffle(samples_v)
+        for i_sample in samples_v:
+            u = cache.slot[i_sample]
+            spec_len = int(cache.spec_len[u])
+            if spec_len <= n_timesteps:
+                continue
+            i_s = np.random.randint(0, spec_len - n_timesteps)
+            rows.append(int(cache.frame_offsets[u]) + i_s)
+            valid.append(n_timesteps)
+            idxs_v.append([i_s, i_s + n_timesteps, int(i_sample)])
+            if len(rows) == batch_size:
+                x, y = cache.gather(("mfcc", "phn"), rows, valid, n_timesteps)
+                yield (x, y, np.array(idxs_v)) if yield_idxs else (x, y)
+                rows, valid, idxs_v = [], [], []

@@ -114,3 +114,57 @@ def _toy_cache(tmp_path, lens):
     return dc.open_cache(path)
 
 
+
+
+# ------------------------------------------------------------------------------------------- window samplers (oracle)
+def test_oracle_window_sampler_follows_the_reference_rng_order(tmp_path):
+    """TIMIT_reader.py:474-523: shuffle once per epoch, skip short utterances, one randint per kept utterance.
+    The oracle's transcription against an independent replay of the same random stream."""
+    lens = [50, 12, 33, 8, 70, 41, 10, 29, 64, 55]
+    cache = _toy_cache(tmp_path, lens)
+    ids = [0, 1, 2, 3, 4, 5, 7, 8, 9]
+    np.random.seed(42)
+    got = list(oracle.window_sampler(cache, ids, n_timesteps=20, batch_size=3, n_epochs=2, yield_idxs=True))
+    np.random.seed(42)
+    order = [str(i) for i in ids]
+    want = []
+    for _ in range(2):
+        np.random.shuffle(order)
+        for s in order:
+            n = lens[int(s)]
+            if n <= 20:
+                continue
+            i_s = np.random.randint(0, n - 20)
+            want.append((i_s, i_s + 20, int(s)))
+    flat = [tuple(r) for b in got for r in b[2]]
+    assert flat == want[: len(flat)] and len(flat) == 3 * (len(want) // 3)
+    x, y, idx = got[0]
+    assert x.shape == (3, 20, 6) and y.shape == (3, 20)
+    i_s, i_e, s = idx[1]
+    assert (x[1] == cache["mfcc"][str(s)][i_s:i_e]).all() and (y[1] == cache["phn"][str(s)][i_s:i_e]).all()
+    cache.close()
+
+
+def test_oracle_spec_window_sampler_split_padding_and_crops(tmp_path):
+    """sound_ds.py:262-350: seed-0 train / validation split, zero padding of short utterances, random crops."""
+    lens = [50, 12, 33, 8, 70, 41, 10, 29, 64, 55]
+    cache = _toy_cache(tmp_path, lens)
+    ids = list(range(10))
+    trn = list(oracle.spec_window_sampler(cache, ids, 20, batch_size=7, randomize_samples=False, sample_trn=True,
+                                          prop_val=0.3, random_seed=5, yield_idxs=True))
+    val = list(oracle.spec_window_sampler(cache, ids, 20, batch_size=3, randomize_samples=False, sample_trn=False,
+                                          prop_val=0.3, random_seed=5, yield_idxs=True))
+    np.random.seed(0)
+    perm = np.arange(10)
+    np.random.shuffle(perm)
+    assert [r[2] for r in trn[0][3]] == list(perm[:-3]) and [r[2] for r in val[0][3]] == list(perm[-3:])
+    mfcc, mel, pdb, idx = trn[0]
+    assert mfcc.shape == (7, 20, 6) and mel.shape == (7, 20, 5) and pdb.shape == (7, 20, 7)
+    for row, (i_s, i_e, s) in enumerate(idx):
+        src = cache["power_dB"][str(s)]
+        if lens[s] <= 20:
+            assert (i_s, i_e) == (0, 20)
+            assert (pdb[row, :lens[s]] == src[:]).all() and (pdb[row, lens[s]:] == 0).all()
+        else:
+            assert (pdb[row] == src[i_s:i_e]).all()
+    cache.close()

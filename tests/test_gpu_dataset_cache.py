@@ -78,3 +78,100 @@ def test_cache_builder_without_labels(al, tmp_path):
     cache = dc.open_cache(path)
     assert len(cache["mfcc"]) == 3 and len(cache["phn"]) == 0
     cache.close()
+
+
+# ------------------------------------------------------------------------------------- window samplers on the device
+def _wide_cache(tmp_path, lens, widths=(80, 80, 201)):
+    """A cache with the hp widths (201 floats per row: windows start on rows that are not 16-byte aligned)."""
+    from speech_cloner_b200 import dataset_cache as dc
+    path = str(tmp_path / "wide_cache.h5py")
+    rng = np.random.default_rng(3)
+    w, _ = dc._open_writer(path, "npz")
+    with w as out:
+        g = {k: out.create_group(k) for k in ("mfcc", "mel_dB", "power_dB", "phn")}
+        for i, n in enumerate(lens):
+            for k, wd in zip(("mfcc", "mel_dB", "power_dB"), widths):
+                g[k].create_dataset(str(i), data=rng.random((n, wd)).astype(np.float32))
+            g["phn"].create_dataset(str(i), data=rng.integers(0, 61, size=n).astype(np.int32))
+    return dc.open_cache(path)
+
+
+@pytest.mark.parametrize("widths,n_t", [((80, 80, 201), 40), ((6, 5, 7), 20), ((80, 80, 201), 33), ((3, 1, 2), 7)])
+def test_spec_window_sampler_equals_the_reference_loop(al, tmp_path, widths, n_t):
+    """Device sampler == literal sound_ds.py:262-350 loop: same [i_s, i_e, i_sample] rows from the same seed, windows
+    and zero padding bit-exact, train and validation split, two epochs."""
+    from speech_cloner_b200 import dataset_cache as dc
+    lens = [50, 12, 133, 8, 70, 41, 10, 29, 64, 155, n_t, n_t + 1, 90, 77]
+    cache = _wide_cache(tmp_path, lens, widths)
+    dev = dc.DeviceSpecCache.from_cache(cache)
+    ids = [i for i in range(len(lens)) if i != 6]
+    for sample_trn in (True, False):
+        kw = dict(batch_size=4, n_epochs=2, randomize_samples=True, sample_trn=sample_trn, prop_val=0.3, random_seed=17,
+                  yield_idxs=True)
+        want = list(oracle.spec_window_sampler(cache, ids, n_t, **kw))
+        state_after = np.random.get_state()[1].copy()
+        got = list(dc.spec_window_sampler(dev, ids, n_t, verbose=False, **kw))
+        assert (np.random.get_state()[1] == state_after).all()             # consumed exactly the same random numbers
+        assert len(got) == len(want) and len(got) > 0
+        padded = 0
+        for g, w in zip(got, want):
+            assert (g[3] == w[3]).all()
+            for a, b in zip(g[:3], w[:3]):
+                assert a.is_cuda and a.dtype.is_floating_point and tuple(a.shape) == b.shape
+                assert (a.cpu().numpy() == b.astype(np.float32)).all()
+            padded += int(sum(lens[s] <= n_t for s in w[3][:, 2]))
+        if sample_trn:
+            assert padded > 0
+    cache.close()
+
+
+def test_window_sampler_equals_the_reference_loop(al, tmp_path):
+    """Device sampler == literal TIMIT_reader.py:474-523 loop (mfcc + phn windows, short utterances skipped)."""
+    from speech_cloner_b200 import dataset_cache as dc
+    lens = [50, 12, 133, 8, 70, 41, 10, 29, 64, 155, 40, 41, 90, 77]
+    cache = _wide_cache(tmp_path, lens)
+    dev = dc.DeviceSpecCache.from_cache(cache)
+    ids = list(range(len(lens)))
+    np.random.seed(9)
+    want = list(oracle.window_sampler(cache, ids, 40, batch_size=5, n_epochs=3, yield_idxs=True))
+    np.random.seed(9)
+    got = list(dc.window_sampler(dev, ids, 40, batch_size=5, n_epochs=3, yield_idxs=True))
+    assert len(got) == len(want) and len(got) > 0
+    for (x, y, idx), (wx, wy, widx) in zip(got, want):
+        assert (idx == widx).all()
+        assert tuple(x.shape) == wx.shape and tuple(y.shape) == wy.shape
+        assert (x.cpu().numpy() == wx).all() and (y.cpu().numpy() == wy).all()
+    cache.close()
+
+
+def test_device_cache_straight_from_the_front_end(al):
+    """A cache that never leaves the GPU: packed front-end outputs wrapped without a copy, windows equal the slices of
+    the per-utterance arrays the public API returns; out-of-range windows are cut, not read."""
+    import torch
+    from speech_cloner_b200 import dataset_cache as dc
+    wavs = synth.batch(5, 21, 1.0) + [synth.utterance(2100, 0.2)]
+    hp = dict(synth.HP_ENC)
+    feats = al.calc_MFCC_input_batch(wavs, **hp)
+    layout = al.FrontendLayout([len(w) for w in wavs], hp["hop_length"])
+    wav_dev = torch.zeros(layout.total_samples, dtype=torch.float32, device="cuda")
+    for w, o in zip(wavs, layout.sample_offsets):
+        wav_dev[o:o + len(w)] = torch.from_numpy(w).cuda()
+    plan = al._plan_from_kwargs(**hp)
+    mfcc, mel, pdb = al.frontend_device(plan, wav_dev, layout)
+    dev = dc.DeviceSpecCache.from_device(mfcc, mel, pdb, layout)
+    assert dev.groups["power_dB"].data_ptr() == pdb.data_ptr()
+    np.random.seed(2)
+    batches = list(dc.spec_window_sampler(dev, range(len(wavs)), 60, batch_size=3, prop_val=0.0, yield_idxs=True,
+                                          verbose=False))
+    assert len(batches) == len(wavs) // 3
+    for m, l, p, idx in batches:
+        for row, (i_s, i_e, s) in enumerate(idx):
+            for got, src in ((m, feats[s][0]), (l, feats[s][1]), (p, feats[s][2])):
+                want = np.zeros((60, src.shape[1]), np.float32)
+                want[:min(60, src.shape[0] - i_s)] = src[i_s:i_e]
+                assert (got[row].cpu().numpy() == want).all()
+    # windows outside the packed rows read nothing
+    out, = dev.gather(("mel_dB",), [dev.n_rows - 2, dev.n_rows + 5, -1], [60, 60, 60], 60)
+    out = out.cpu().numpy()
+    assert (out[0, :2] == mel[-2:].cpu().numpy()).all() and (out[0, 2:] == 0).all() and (out[1:] == 0).all()
+
