@@ -5,11 +5,11 @@ This module is the *checker*, never the product: only ``tests/``,
 legs may import it.  The product path (``speech_cloner_b200``) never imports anything
 from ``oracle/`` and fails loudly when its CUDA library is missing.
 
-PARITY UNPINNED BY THE REFERENCE.  The reference (``/root/reference/audio_lib.py``)
-delegates its arithmetic to librosa (un-vendored, un-pinned, 0.6.x by API usage:
-``librosa.filters.dct`` at audio_lib.py:176, ``librosa.output.write_wav`` at
-test.py:177) and scipy.signal.  librosa cannot be imported or installed in this image,
-the reference ships no tests / golden vectors, so this file restates
+PARITY PINNED TO THE REFERENCE SOURCE FOR ITS OWN CODE, UNPINNED FOR LIBROSA'S.  The reference
+(``/root/reference/audio_lib.py``) delegates its transforms to librosa (un-vendored, un-pinned,
+0.6.x by API usage: ``librosa.filters.dct`` at audio_lib.py:176, ``librosa.output.write_wav`` at
+test.py:177) and scipy.signal; librosa cannot be imported or installed in this image and the
+reference ships no tests / golden vectors.  So this file restates
 
   * ``audio_lib.py:12-47``   pre-/de-emphasis                (scipy.signal.lfilter)
   * ``audio_lib.py:51-85``   phoneme frame labels            (integer logic)
@@ -19,9 +19,19 @@ the reference ships no tests / golden vectors, so this file restates
   * ``audio_lib.py:278-308`` ``from_power_to_wav``           (librosa db_to_power)
 
 with the published librosa-0.6 algorithms, written with explicit dtypes so that NumPy 2
-scalar-promotion rules cannot change a result.  The independent pins are in
-``tests/test_oracle_pins.py`` (torch.stft, transformers.audio_utils, scipy.fft.dct,
-torchaudio) and the frozen known-answer vectors in ``tests/golden/``.
+scalar-promotion rules cannot change a result.  Two kinds of pins:
+
+  1. the reference file ITSELF, imported unmodified from /root/reference with a librosa shim in
+     sys.modules (``tests/golden/librosa_shim.py``), is run on seeded inputs by
+     ``tests/golden/make_reference_vectors.py``; its outputs are frozen in
+     ``tests/golden/reference_run_vectors.npz`` and this oracle reproduces them bit for bit
+     (``tests/test_reference_run.py``).  That pins everything audio_lib.py does in its own code:
+     gain, emphasis filters, dtype chain, normalisation, deltas, clipping, the Griffin-Lim loop with
+     its ``np.random.rand`` phase, ``realse``, the label loop.
+  2. the librosa primitives underneath (stft, istft, filters.mel, filters.dct, the dB helpers) have
+     no reference-held check; they are pinned piecewise against independent implementations in
+     ``tests/test_oracle_pins.py`` (torch.stft / istft, transformers.audio_utils, scipy.fft.dct,
+     torchaudio) and by the frozen known-answer vectors in ``tests/golden/oracle_vectors.npz``.
 
 dtype chain restated from the reference era (NumPy 1.x + librosa 0.6 + scipy.fftpack):
   gain            float32 array * float32 scalar                      audio_lib.py:126

@@ -2,10 +2,10 @@
 
     python tests/golden/make_golden.py
 
-PARITY UNPINNED BY THE REFERENCE: /root/reference ships no tests or vectors and its audio_lib cannot be
-imported here (librosa / matplotlib absent, no network), so these vectors freeze the ORACLE
-(oracle/audio_lib_oracle.py, pinned piecewise against torch.stft / transformers / scipy / torchaudio in
-tests/test_oracle_pins.py).  They guard both the oracle and the CUDA path against drift.
+These vectors freeze the ORACLE (oracle/audio_lib_oracle.py): /root/reference ships no tests or vectors of its own.  The
+oracle is pinned to the reference file's own run by make_reference_vectors.py / tests/test_reference_run.py and, for the
+librosa primitives, piecewise against torch.stft / transformers / scipy / torchaudio in tests/test_oracle_pins.py.
+They guard both the oracle and the CUDA path against drift.
 Inputs are regenerated from seeds by speech_cloner_b200.synth, so only outputs are stored.
 """
 import os
