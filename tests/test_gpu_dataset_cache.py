@@ -175,3 +175,68 @@ def test_device_cache_straight_from_the_front_end(al):
     out = out.cpu().numpy()
     assert (out[0, :2] == mel[-2:].cpu().numpy()).all() and (out[0, 2:] == 0).all() and (out[1:] == 0).all()
 
+
+
+# -------------------------------------------------- against the reference's own caller code (reference_caller_vectors.npz)
+def _ref_batches(G, prefix, names):
+    out, b = [], 0
+    while f"{prefix}/{b}/idxs" in G.files:
+        out.append(tuple(G[f"{prefix}/{b}/{n}"] for n in names))
+        b += 1
+    return out
+
+
+def test_device_samplers_equal_the_reference_methods(al):
+    """Sound_DS.spec_window_sampler / TIMIT.window_sampler executed from the reference files (ast-cut, unmodified) vs
+    the device samplers on the same cache, seeds and arguments: same rows, same windows, same random numbers consumed."""
+    from speech_cloner_b200 import dataset_cache as dc
+    from tests.golden import make_reference_caller_vectors as mc
+    G = np.load(mc.OUT)
+    cache = mc.sampler_cache("mem://gpu")
+    keys = [str(i) for i in range(len(mc.SAMPLER_LENS))]
+    dev = dc.DeviceSpecCache.from_arrays({g: [cache[g][k] for k in keys] for g in ("mfcc", "mel_dB", "power_dB", "phn")}, keys)
+    ids = np.arange(len(mc.SAMPLER_LENS))[mc.sampler_filter()]
+    for r, kw in enumerate(mc.SPEC_RUNS):
+        want = _ref_batches(G, f"spec{r}", ("mfcc", "mel_dB", "power_dB", "idxs"))
+        got = list(dc.spec_window_sampler(dev, ids, mc.N_TIMESTEPS, random_seed=mc.RANDOM_SEED, yield_idxs=True,
+                                          verbose=False, **kw))
+        assert len(got) == len(want) > 0
+        for g, w in zip(got, want):
+            assert np.array_equal(g[3], w[3])
+            for a, b in zip(g[:3], w[:3]):
+                assert np.array_equal(a.cpu().numpy(), b.astype(np.float32))       # padded reference windows are float64
+        assert np.array_equal(np.random.get_state()[1][:8], G[f"spec{r}/rng_after"])
+    for r, kw in enumerate(mc.WIN_RUNS):
+        want = _ref_batches(G, f"win{r}", ("x", "y", "idxs"))
+        np.random.seed(100 + r)
+        got = list(dc.window_sampler(dev, ids, mc.N_TIMESTEPS, yield_idxs=True, **kw))
+        assert len(got) == len(want) > 0
+        for (x, y, idx), (wx, wy, widx) in zip(got, want):
+            assert np.array_equal(idx, widx) and np.array_equal(x.cpu().numpy(), wx) and np.array_equal(y.cpu().numpy(), wy)
+
+
+def test_cache_builder_equals_the_reference_method(al, tmp_path):
+    """TIMIT.create_phn_mfcc_cache executed from the reference file (around the reference's audio_lib under the librosa
+    shim) vs build_spec_cache on the GPU: same groups and keys, features within 1e-4 / 1e-5, labels exact."""
+    from speech_cloner_b200 import dataset_cache as dc
+    from tests.golden import make_reference_caller_vectors as mc
+    G = np.load(mc.OUT)
+    wavs, phn_vs = mc.cache_inputs()
+    path = str(tmp_path / "cache.h5py")
+    dc.build_spec_cache({"wav": wavs, "phn_v": phn_vs}, mc.CFG, path, phn_conv_d=mc.mr.PHN_CONV, fmt="npz")
+    cache = dc.open_cache(path)
+    for i in range(len(wavs)):
+        for g in ("mfcc", "mel_dB", "power_dB"):
+            assert_close(cache[g][str(i)], G[f"cache/{g}/{i}"], what=f"{g}/{i}")
+        assert np.array_equal(cache["phn"][str(i)], G[f"cache/phn/{i}"])
+    cache.close()
+
+
+def test_compound_on_device_equals_the_reference_function(al):
+    import torch
+    from speech_cloner_b200 import conversion as cv
+    from tests.golden import make_reference_caller_vectors as mc
+    G = np.load(mc.OUT)
+    for i, (y0, y1) in enumerate(mc.compound_inputs()):
+        got = cv.compound(torch.from_numpy(y0).cuda(), torch.from_numpy(y1).cuda())
+        assert np.array_equal(got.cpu().numpy(), G[f"compound{i}/out"])
