@@ -15,9 +15,6 @@ namespace scdsp {
 #ifndef SC_GL_SPLIT_TASKS
 #define SC_GL_SPLIT_TASKS 0      // 1: packed columns c = 0 on warp 0 and c = 10 on warp 1 (each next to one-frame columns)
 #endif
-#ifndef SC_GL_PDL
-#define SC_GL_PDL 1              // iterations of one call chained by programmatic dependent launch (speechdsp.cu)
-#endif
 constexpr int kGlFrames = 32;                          // frames per tile (16 units x 2)
 constexpr int kGlOutHops = kGlFrames - 4;              // complete hops per tile
 constexpr int kGlOut = kGlOutHops * kHop;              // 2240 output samples per tile
@@ -285,10 +282,6 @@ k_gl_iter_persist(const GlJob* __restrict__ jobs, const int2* __restrict__ tile_
     };
 
     int tile = blockIdx.x, b = 0;
-#if SC_GL_PDL
-    griddep_launch();                 // the next iteration may take an SM slot as soon as a CTA of this one exits ...
-    griddep_wait();                   // ... and waits here, tables loaded, until the previous iteration's waveform is complete
-#endif
     if (tile < n_tiles) stage(tile, 0);
     cp_async_wait_all();
     __syncthreads();

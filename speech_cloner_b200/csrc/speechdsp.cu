@@ -1206,26 +1206,6 @@ static GlTables gl_tables(const sc_plan* pl) {
 }
 
 // one launch of the one-tile-per-CTA kernels: initial inverse STFT (init) or a plain iteration
-// One launch of the persistent iteration kernel.  `chained`: the launch directly before it in the stream is the previous
-// iteration, so it may overlap that launch's drain (programmatic dependent launch; the kernel waits for the previous
-// waveform with griddepcontrol.wait before its first read).
-static int gl_persist_launch(int grid, cudaStream_t st, bool chained, const GlJob* jobs, const int2* tab, int n_tiles,
-                             GlTables tb, const float* amp, const float* wav_in, float* wav_out) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(kFeThreads);
-    cfg.dynamicSmemBytes = sizeof(GlSmemP);
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = (SC_GL_PDL && chained) ? 1 : 0;
-    SC_CUDA(cudaLaunchKernelEx(&cfg, k_gl_iter_persist, jobs, tab, n_tiles, tb, amp, wav_in, wav_out));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return SC_OK;
-}
-
 static int gl_launch(sc_plan* pl, bool init, const GlJob* jobs, int n, const int32_t* prefix, int n_tiles,
                      const float* amp, const float* phase0, const float* wav_in, float* wav_out, cudaStream_t st) {
     if (n_tiles == 0) return SC_OK;
@@ -1308,8 +1288,9 @@ extern "C" int sc_griffinlim_batch(sc_plan* pl, const float* amp, const float* p
     for (int i = 1; i < n_iters; ++i) {
         if (pl->fast && prefix[n] > 0) {
             const int grid = prefix[n] < 2 * n_sm ? prefix[n] : 2 * n_sm;
-            if (int rc = gl_persist_launch(grid, st, /*chained=*/i > 1 && !rms, dj, at<int2>(pl, o_tab), prefix[n], gl_tables(pl),
-                                           amp, buf(i - 1), buf(i))) return rc;
+            k_gl_iter_persist<<<grid, kFeThreads, sizeof(GlSmemP), st>>>(dj, at<int2>(pl, o_tab), prefix[n], gl_tables(pl), amp,
+                                                                         buf(i - 1), buf(i));
+            SC_LAUNCHED();
         } else if (int rc = gl_launch(pl, false, dj, n, dp, prefix[n], amp, phase0, buf(i - 1), buf(i), st)) return rc;
         if (rms && rprefix[n] > 0) {
             k_rms_delta_partial<<<rprefix[n], 256, 0, st>>>(buf(i - 1), buf(i), dj, n, at<int32_t>(pl, o_r), rpart);
@@ -1368,8 +1349,8 @@ extern "C" int sc_griffinlim_chunk_run(sc_plan* pl, const float* amp, const floa
         if (pl->fast && !init) {
             // persistent iteration kernel (one job: no tile table needed)
             const int grid = tiles < 2 * pl->n_sm ? tiles : 2 * pl->n_sm;
-            const bool chained = m > 0 && !(m == 1 && phase0 != nullptr);      // the launch before it is a persistent step
-            if (int rc = gl_persist_launch(grid, st, chained, dj + m, nullptr, tiles, gl_tables(pl), amp, in, out)) return rc;
+            k_gl_iter_persist<<<grid, kFeThreads, sizeof(GlSmemP), st>>>(dj + m, nullptr, tiles, gl_tables(pl), amp, in, out);
+            SC_LAUNCHED();
         } else if (int rc = gl_launch(pl, init, dj + m, 1, dp + 2 * m, tiles, amp, phase0, in, out, st)) return rc;
     }
     return SC_OK;
