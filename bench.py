@@ -565,6 +565,35 @@ def main():
                  "frac_hbm_compute": FE_BYTES_PER_FRAME * (6000 * 601 + 4500 * 801) / world / (sw_c * 1e-3) / 1e9 / peak}
         del sdev, sout, gathered
 
+    # ---- window sampler on the device-resident features of the step (every rank its own cache)
+    wsamp = None
+    try:
+        from speech_cloner_b200 import dataset_cache as dc
+        cache = dc.DeviceSpecCache.from_device(out[0], out[1], out[2], lay)
+        n_t, n_w = 400, 2048                                          # 2 048 windows of 400 frames = 1.18 GB per launch
+        rs = np.random.RandomState(5)
+        u = rs.randint(0, N_UTTS, size=n_w)
+        first = cache.frame_offsets[u] + rs.randint(0, np.asarray(cache.spec_len)[u] - n_t)
+        valid = np.full(n_w, n_t, np.int32)
+        cache.gather(dc.DeviceSpecCache.FEATURES, first, valid, n_t)
+        ws_ms, _ = timed(lambda: cache.gather(dc.DeviceSpecCache.FEATURES, first, valid, n_t), 3)
+        ws_bytes = 2 * 4 * n_w * n_t * sum(out_i.shape[1] for out_i in out)
+        np.random.seed(3)
+        barrier()
+        t0 = time.perf_counter()
+        nb = sum(1 for _ in dc.spec_window_sampler(cache, range(N_UTTS), n_t, batch_size=32, n_epochs=4, prop_val=0.0,
+                                                   verbose=False))
+        torch.cuda.synchronize()
+        ws_batch_us = 1e6 * (time.perf_counter() - t0) / max(nb, 1)
+        wsamp = {"workload": f"{n_w} random windows x {n_t} frames x (80 + 80 + 201) float32 out of the step's packed outputs, "
+                             "one sc_window_gather launch (incl. the index upload and output allocation of DeviceSpecCache.gather)",
+                 "ms": ws_ms, "achieved": ws_bytes / (ws_ms * 1e-3) / 1e9, "unit": "GB/s", "peak": peak,
+                 "frac": ws_bytes / (ws_ms * 1e-3) / 1e9 / peak, "bytes": "windows read + written",
+                 "us_per_32_window_batch_through_spec_window_sampler": ws_batch_us, "ranks": world}
+        del cache
+    except Exception as e:                                            # never lose the bench line to a side leg
+        wsamp = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- distributed parity self-check on this run's ranks (the 1-GPU test run cannot see these)
     selfcheck = None
     if not args.no_selfcheck and gl is not None:
@@ -646,7 +675,7 @@ def main():
                        "parallelism": f"utterance shards, {world} rank(s), no data-path collective",
                        "cpu_binding_rank0": f"{bind['action']}: {bind['why']}"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "frontend_fp32_mode": alt, "griffin_lim": gl, "sweep_10h": sweep, "parity_selfcheck": selfcheck,
+            "frontend_fp32_mode": alt, "griffin_lim": gl, "sweep_10h": sweep, "window_sampler": wsamp, "parity_selfcheck": selfcheck,
         }
         emit(line)
     if world > 1:
