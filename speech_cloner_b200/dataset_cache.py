@@ -275,9 +275,10 @@ class DeviceSpecCache:
         return cls.from_arrays({g: [cache[g][k][...] for k in keys] for g in groups}, keys)
 
     # -- one batch
-    def gather(self, names, first_rows, valid_rows, n_timesteps):
+    def gather(self, names, first_rows, valid_rows, n_timesteps, out=None):
         """Windows ``[first_rows[w], +valid_rows[w])`` of the packed rows, zero padded to ``n_timesteps`` rows, from every
-        group in ``names``: dense ``[n_windows, n_timesteps(, width)]`` CUDA tensors out of one launch."""
+        group in ``names``: dense ``[n_windows, n_timesteps(, width)]`` CUDA tensors out of one launch (written into
+        ``out``, a matching list of tensors, when given)."""
         torch = self._torch
         lib = _lib.load()
         n_w = len(first_rows)
@@ -287,11 +288,17 @@ class DeviceSpecCache:
         host[2 * n_w:] = np.asarray(valid_rows, dtype=np.int32)
         dev = stage.to("cuda", non_blocking=True)
         outs, srcs, dsts, widths = [], [], [], []
-        for name in names:
+        for a, name in enumerate(names):
             t = self.groups[name]
-            out = torch.empty((n_w, int(n_timesteps)) + tuple(t.shape[1:]), dtype=t.dtype, device="cuda")
-            outs.append(out)
-            srcs.append(t.data_ptr()); dsts.append(out.data_ptr()); widths.append(int(np.prod(t.shape[1:], dtype=np.int64)))
+            shape = (n_w, int(n_timesteps)) + tuple(t.shape[1:])
+            if out is None:
+                o = torch.empty(shape, dtype=t.dtype, device="cuda")
+            else:
+                o = out[a]
+                if tuple(o.shape) != shape or o.dtype != t.dtype or not (o.is_cuda and o.is_contiguous()):
+                    raise ValueError(f"out[{a}]: contiguous CUDA tensor of shape {shape} and dtype {t.dtype} expected")
+            outs.append(o)
+            srcs.append(t.data_ptr()); dsts.append(o.data_ptr()); widths.append(int(np.prod(t.shape[1:], dtype=np.int64)))
         for a0 in range(0, len(names), 4):
             k = len(names[a0:a0 + 4])
             rc = lib.sc_window_gather((_lib.C.c_void_p * k)(*srcs[a0:a0 + k]), (_lib.C.c_void_p * k)(*dsts[a0:a0 + k]),

@@ -174,6 +174,13 @@ def test_device_cache_straight_from_the_front_end(al):
     out, = dev.gather(("mel_dB",), [dev.n_rows - 2, dev.n_rows + 5, -1], [60, 60, 60], 60)
     out = out.cpu().numpy()
     assert (out[0, :2] == mel[-2:].cpu().numpy()).all() and (out[0, 2:] == 0).all() and (out[1:] == 0).all()
+    # caller-owned output tensors are filled in place; a wrong shape is rejected
+    buf = [torch.full((2, 30, 80), 7.0, device="cuda"), torch.full((2, 30, 201), 7.0, device="cuda")]
+    res = dev.gather(("mfcc", "power_dB"), [3, 11], [30, 4], 30, out=buf)
+    assert res[0].data_ptr() == buf[0].data_ptr() and torch.equal(buf[1][0], pdb[3:33]) and torch.equal(buf[0][1, :4], mfcc[11:15])
+    assert float(buf[0][1, 4:].abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        dev.gather(("mfcc",), [0], [30], 30, out=[torch.empty((1, 31, 80), device="cuda")])
 
 
 
