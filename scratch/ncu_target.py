@@ -1,4 +1,5 @@
-"""Small profiling target: 2 front-end steps (config-2 shape) + a 4-iteration Griffin-Lim (config-3 shape)."""
+"""Small profiling target: 2 front-end steps (config-2 shape), a 2 048-window sampler gather out of their outputs and a
+4-iteration Griffin-Lim (config-3 shape)."""
 import sys; sys.path.insert(0, '.')
 import numpy as np, torch
 from speech_cloner_b200 import audio_lib as al, synth
@@ -17,6 +18,14 @@ for w, o in zip(wavs, lay.sample_offsets):
 for _ in range(2):
     out = al.frontend_device(plan, dev, lay)
 torch.cuda.synchronize()
+from speech_cloner_b200 import dataset_cache as dc
+cache = dc.DeviceSpecCache.from_device(out[0], out[1], out[2], lay)
+rs = np.random.RandomState(5)
+u = rs.randint(0, 256, size=2048)
+first = cache.frame_offsets[u] + rs.randint(0, np.asarray(cache.spec_len)[u] - 400)
+win = cache.gather(dc.DeviceSpecCache.FEATURES, first, np.full(2048, 400, np.int32), 400)
+torch.cuda.synchronize()
+del win
 glay = al._GlLayout([1000] * 64, 80)
 gplan = al.DspPlan.get(n_fft=400, win_length=400, hop_length=80)
 amp = torch.rand((glay.frame_offsets[-1], 201), device="cuda") * 0.1
