@@ -281,42 +281,48 @@ k_gl_iter_persist(const GlJob* __restrict__ jobs, const int2* __restrict__ tile_
         }
     };
 
+    // step 1 of a tile: windowed frame pair of this unit -> first 20-point transforms -> exchange slots.
+    // Frames that do not exist (outside [0, T) or outside the rows this job holds) are fed exact zeros end to end: the
+    // two frames of a pair share one packed transform, so any garbage in the partner would change the rounding of the
+    // real frame and break the bit-identity of time-chunked runs.
+    auto step1 = [&](const GlJob& job, const GlGeom& g, const float* __restrict__ span) {
+        const int fa = g.t0 + 2 * unit, fb = fa + 1;
+        const bool va = fa >= job.f_lo && fa < job.f_lo + job.f_cnt && fa < g.T;
+        const bool vb = fb >= job.f_lo && fb < job.f_lo + job.f_cnt && fb < g.T;
+        const float ka = va ? 1.0f : 0.0f, kb = vb ? 1.0f : 0.0f;
+        float s[24];
+        const float* __restrict__ src = span + unit * (2 * kHop) + j;
+#pragma unroll
+        for (int m = 0; m < 24; ++m) s[m] = src[20 * m];
+        float xa[20], xb[20];
+#pragma unroll
+        for (int n1 = 0; n1 < 20; ++n1) {
+            const float w = sm.win_half[20 * n1 + j];
+            xa[n1] = s[n1] * (w * ka);
+            xb[n1] = s[n1 + 4] * (w * kb);
+        }
+        fwd_step1_real(xa, xb, tw, unit_slots + j);
+    };
+
+    // Three CTA-wide barriers per tile: the overlap-add gather of tile i (shared loads + global stores) and step 1 of
+    // tile i+1 (shared loads + FMAs) touch different buffers (seg / next span -> slots) and run as one phase.
     int tile = blockIdx.x, b = 0;
     if (tile < n_tiles) stage(tile, 0);
     cp_async_wait_all();
     __syncthreads();
+    if (tile < n_tiles) {
+        const GlJob job0 = sm.job[0];
+        step1(job0, gl_geom(job0, sm.ent[0].y), sm.span[0]);
+    }
+    __syncthreads();
 #pragma unroll 1
     for (; tile < n_tiles; tile += gridDim.x, b ^= 1) {
-        const int2 e = sm.ent[b];                     // written by stage() one iteration (and one barrier) ago
+        const int2 e = sm.ent[b];                     // written by stage() one iteration (and at least one barrier) ago
         const GlJob job = sm.job[b];
-        if (tile + (int)gridDim.x < n_tiles) stage(tile + gridDim.x, b ^ 1);
+        const bool has_next = tile + (int)gridDim.x < n_tiles;
+        if (has_next) stage(tile + gridDim.x, b ^ 1);
         const GlGeom g = gl_geom(job, e.y);
         const int T = g.T, Lw = g.Lw, out_first = g.out_first, out_end = g.out_end, t0 = g.t0, span0 = g.span0;
-        const float* __restrict__ span = sm.span[b];
-
-        // Frames of this unit.  A frame that does not exist (outside [0, T) or outside the rows this job
-        // holds) is fed exact zeros end to end: the two frames of a pair share one packed transform, so
-        // any garbage in the partner would change the rounding of the real frame and break the
-        // bit-identity of time-chunked runs.
-        const int fa = t0 + 2 * unit, fb = fa + 1;
-        const bool va = fa >= job.f_lo && fa < job.f_lo + job.f_cnt && fa < T;
-        const bool vb = fb >= job.f_lo && fb < job.f_lo + job.f_cnt && fb < T;
-        const float ka = va ? 1.0f : 0.0f, kb = vb ? 1.0f : 0.0f;
-        {
-            float s[24];
-            const float* __restrict__ src = span + unit * (2 * kHop) + j;
-    #pragma unroll
-            for (int m = 0; m < 24; ++m) s[m] = src[20 * m];
-            float xa[20], xb[20];
-    #pragma unroll
-            for (int n1 = 0; n1 < 20; ++n1) {
-                const float w = sm.win_half[20 * n1 + j];
-                xa[n1] = s[n1] * (w * ka);
-                xb[n1] = s[n1 + 4] * (w * kb);
-            }
-            fwd_step1_real(xa, xb, tw, unit_slots + j);
-            __syncthreads();
-        }
         {
             // step-2 task of this thread (packed columns on warp 0, see step2_task) and its unit's two frames
             int u2, c2;
@@ -335,25 +341,24 @@ k_gl_iter_persist(const GlJob* __restrict__ jobs, const int2* __restrict__ tile_
             inv_step2(v, row);                          // a slot row is read and rewritten by the same thread only
         }
         __syncthreads();
-        float comb[24];
+        float* seg = sm.seg;
         {
+            float comb[24];
             float ya[20], yb[20];
             inv_step1_real(ya, yb, tw, unit_slots + j);
-    #pragma unroll
+#pragma unroll
             for (int m = 0; m < 24; ++m) {
                 float a = 0.f;
                 if (m < 20) a = ya[m] * sm.win_inv[20 * m + j];
                 if (m >= 4) a += yb[m - 4] * sm.win_inv[20 * (m - 4) + j];
                 comb[m] = a;
             }
-        }
-        float* seg = sm.seg;
-        {
             float* __restrict__ dst = seg + unit * kGlSeg + j;
-    #pragma unroll
+#pragma unroll
             for (int m = 0; m < 24; ++m) dst[20 * m] = comb[m];
         }
-        __syncthreads();
+        cp_async_wait_all();                            // this thread's part of the next span has landed ...
+        __syncthreads();                                // ... and everybody's is visible; seg complete; slots free
         // ---- ordered overlap-add gather + normalisation; local positions [320, 320 + kGlOut) are complete
         {
             float* __restrict__ dst = wav_out + job.wav_out_off;
@@ -389,7 +394,10 @@ k_gl_iter_persist(const GlJob* __restrict__ jobs, const int2* __restrict__ tile_
                 dst[s - out_first] = acc * nrm;
             }
         }
-        cp_async_wait_all();
+        if (has_next) {
+            const GlJob jn = sm.job[b ^ 1];
+            step1(jn, gl_geom(jn, sm.ent[b ^ 1].y), sm.span[b ^ 1]);
+        }
         __syncthreads();
     }
 }
