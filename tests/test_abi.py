@@ -71,3 +71,22 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_window_gather_argument_checks_need_no_gpu(built_lib):
+    """sc_window_gather validates its host arguments before any CUDA call: bad calls are SC_ERR_INVALID with a message,
+    an empty batch is a no-op (sound_ds.py:262-350 never yields an empty batch, but the ABI must not launch one)."""
+    from speech_cloner_b200 import _lib
+    lib = _lib.load()
+    P = C.c_void_p
+    src, dst = (P * 1)(0x1000), (P * 1)(0x2000)
+    w1, w0 = (C.c_int64 * 1)(80), (C.c_int64 * 1)(0)
+    dev = P(0x3000)
+
+    def call(s=src, d=dst, w=w1, n_arrays=1, rows=10, first=dev, valid=dev, n_windows=0, n_t=4):
+        return lib.sc_window_gather(s, d, w, n_arrays, rows, first, valid, n_windows, n_t, None)
+    assert call() == _lib.SC_OK                                       # zero windows: nothing is launched
+    for bad in (dict(n_arrays=0), dict(n_arrays=5), dict(w=w0), dict(n_t=0), dict(n_windows=-1), dict(rows=-1),
+                dict(first=None), dict(valid=None), dict(s=(P * 1)(0)), dict(d=(P * 1)(0x2002))):
+        assert call(**bad) == _lib.SC_ERR_INVALID, bad
+        assert b"sc_window_gather" in lib.sc_last_error()
