@@ -316,6 +316,44 @@ def _has_group(cache, name) -> bool:
         return False
 
 
+class _BatchPlan:
+    """Rows of one batch under construction: first packed row, valid rows and the reference's index triple per window."""
+
+    def __init__(self, cache: "DeviceSpecCache", n_timesteps: int, batch_size: int):
+        self.cache, self.n_t, self.size = cache, int(n_timesteps), int(batch_size)
+        self.clear()
+
+    def clear(self):
+        self.first_rows, self.valid_rows, self.triples = [], [], []
+
+    def add(self, slot: int, start: int, valid: int, sample_id: int) -> bool:
+        """Append the window ``[start, start + n_timesteps)`` of utterance ``slot``; True when the batch is full."""
+        self.first_rows.append(int(self.cache.frame_offsets[slot]) + start)
+        self.valid_rows.append(valid)
+        self.triples.append([start, start + self.n_t, sample_id])
+        return len(self.first_rows) == self.size
+
+    def launch(self, names, yield_idxs: bool):
+        tensors = tuple(self.cache.gather(names, self.first_rows, self.valid_rows, self.n_t))
+        out = tensors + (np.array(self.triples),) if yield_idxs else tensors
+        self.clear()
+        return out
+
+
+def _reference_split(keys: np.ndarray, prop_val: float, sample_trn: bool, random_seed) -> np.ndarray:
+    """The train / validation split of sound_ds.py:269-284: a seed-0 permutation whose last ``int(prop_val * n)`` entries
+    are the validation set, then the generator is re-seeded with the reader's ``random_seed``."""
+    if prop_val <= 0.0:
+        return keys
+    np.random.seed(0)
+    perm = np.arange(keys.shape[0])
+    np.random.shuffle(perm)
+    n_val = int(prop_val * keys.shape[0])
+    picked = keys[perm[:-n_val]] if sample_trn else keys[perm[-n_val:]]
+    np.random.seed(random_seed)
+    return picked
+
+
 def spec_window_sampler(cache: DeviceSpecCache, sample_ids, n_timesteps, batch_size=32, n_epochs=1,
                         randomize_samples=True, sample_trn=True, prop_val=0.3, random_seed=None, yield_idxs=False,
                         verbose=True):
@@ -328,37 +366,25 @@ def spec_window_sampler(cache: DeviceSpecCache, sample_ids, n_timesteps, batch_s
     ``np.random.randint(0, spec_len - n_timesteps)`` per utterance longer than the window; shorter ones are zero padded
     without a draw.  (The reference's padded windows are float64 because of ``np.zeros``; the values are the same.)
     """
-    samples_v = np.array([str(int(i)) for i in sample_ids])       # a NumPy array of str, like the reference
-    if prop_val > 0.0:
-        np.random.seed(0)
-        idx_v = np.arange(samples_v.shape[0])
-        np.random.shuffle(idx_v)
-        n_val = int(prop_val * samples_v.shape[0])
-        samples_v = samples_v[idx_v[:-n_val]] if sample_trn else samples_v[idx_v[-n_val:]]
-        np.random.seed(random_seed)
-    rows, valid, idxs_v, n_warning = [], [], [], 0
+    # a NumPy array of str keys: np.random.shuffle must permute the same container type as the reference's
+    keys = _reference_split(np.array([str(int(i)) for i in sample_ids]), prop_val, sample_trn, random_seed)
+    plan = _BatchPlan(cache, n_timesteps, batch_size)
+    padded_notes = 0
     for _ in range(n_epochs):
         if randomize_samples:
-            np.random.shuffle(samples_v)
-        for i_sample in samples_v:
-            u = cache.slot[str(i_sample)]
-            spec_len = int(cache.spec_len[u])
-            if spec_len <= n_timesteps:
-                i_s, i_e = 0, n_timesteps
-                valid.append(spec_len)
-                if verbose and n_warning < 5:
+            np.random.shuffle(keys)
+        for key in keys:
+            slot = cache.slot[str(key)]
+            frames = int(cache.spec_len[slot])
+            if frames > n_timesteps:
+                start, valid = np.random.randint(0, frames - n_timesteps), n_timesteps
+            else:                                                 # zero padded, no random number consumed (:301-311)
+                start, valid = 0, frames
+                if verbose and padded_notes < 5:
                     print("WARNING: padding!!!")
-                    n_warning += 1
-            else:
-                i_s = np.random.randint(0, spec_len - n_timesteps)
-                i_e = i_s + n_timesteps
-                valid.append(n_timesteps)
-            rows.append(int(cache.frame_offsets[u]) + i_s)
-            idxs_v.append([i_s, i_e, int(i_sample)])
-            if len(rows) == batch_size:
-                out = tuple(cache.gather(DeviceSpecCache.FEATURES, rows, valid, n_timesteps))
-                yield out + (np.array(idxs_v),) if yield_idxs else out
-                rows, valid, idxs_v = [], [], []
+                    padded_notes += 1
+            if plan.add(slot, start, valid, int(key)):
+                yield plan.launch(DeviceSpecCache.FEATURES, yield_idxs)
 
 
 def window_sampler(cache: DeviceSpecCache, sample_ids, n_timesteps, batch_size=32, n_epochs=1, randomize_samples=True,
@@ -366,21 +392,15 @@ def window_sampler(cache: DeviceSpecCache, sample_ids, n_timesteps, batch_size=3
     """``TIMIT.window_sampler`` (TIMIT_reader.py:474-523) on a device-resident cache: ``(x_v, y_v[, idxs_v])`` with the
     mfcc windows ``[batch_size, n_timesteps, width]`` and the phoneme targets ``[batch_size, n_timesteps(, k)]`` as CUDA
     tensors.  Utterances with ``spec_len <= n_timesteps`` are skipped without consuming a random number."""
-    samples_v = [str(int(i)) for i in sample_ids]                 # a Python list, like the reference
-    rows, valid, idxs_v = [], [], []
+    keys = [str(int(i)) for i in sample_ids]                      # a Python list here: the reference shuffles a list (:478)
+    plan = _BatchPlan(cache, n_timesteps, batch_size)
     for _ in range(n_epochs):
         if randomize_samples:
-            np.random.shuffle(samples_v)
-        for i_sample in samples_v:
-            u = cache.slot[i_sample]
-            spec_len = int(cache.spec_len[u])
-            if spec_len <= n_timesteps:
+            np.random.shuffle(keys)
+        for key in keys:
+            slot = cache.slot[key]
+            frames = int(cache.spec_len[slot])
+            if frames <= n_timesteps:
                 continue
-            i_s = np.random.randint(0, spec_len - n_timesteps)
-            rows.append(int(cache.frame_offsets[u]) + i_s)
-            valid.append(n_timesteps)
-            idxs_v.append([i_s, i_s + n_timesteps, int(i_sample)])
-            if len(rows) == batch_size:
-                x, y = cache.gather(("mfcc", "phn"), rows, valid, n_timesteps)
-                yield (x, y, np.array(idxs_v)) if yield_idxs else (x, y)
-                rows, valid, idxs_v = [], [], []
+            if plan.add(slot, np.random.randint(0, frames - n_timesteps), n_timesteps, int(key)):
+                yield plan.launch(("mfcc", "phn"), yield_idxs)
