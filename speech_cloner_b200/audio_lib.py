@@ -682,7 +682,12 @@ def from_power_to_wav_batch(Ps, P_dB_norm_factor=0.01, pre_emphasis=0.97, hop_le
         for out, layout in parts:
             outs += [out[o:o + m] for o, m in zip(layout.sample_offsets, layout.samples)]
         return outs
+    # librosa.stft inside the reference's loop (audio_lib.py:267) rejects a non-finite waveform: NaN / Inf input maps, or an
+    # all-zero map with realse != 1 (0 / 0 at :296), raise there from the second iteration on
+    finite = torch.stack([torch.isfinite(out).all() for out, _ in parts]).all() if int(n_iter) >= 2 else None
     hosts = _to_host(torch, *[out for out, _ in parts])
+    if finite is not None and not bool(finite):
+        raise ValueError("Audio buffer is not finite everywhere")
     for host, (_, layout) in zip(hosts, parts):
         outs += [host[o:o + m] for o, m in zip(layout.sample_offsets, layout.samples)]
     return outs

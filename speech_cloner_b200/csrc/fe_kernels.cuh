@@ -68,7 +68,12 @@ __host__ __device__ inline int abs_depth(int64_t n) {
 // order (x + 0 = x exactly for the non-negative sums).  The staged copy is padded by 4 words per 128 samples so
 // that leaves that start 128 samples apart fall into different bank groups.
 constexpr int kAbs3Threads = 128;
-constexpr int kAbs3Smem = kAbsSubtree + 4 * (kAbsSubtree / 128 + 1);
+// NumPy splits at n/2 rounded DOWN to a multiple of 8, so the right child of a node is up to 8 samples larger than half of
+// it: a sub-tree at depth abs_depth(n) can hold up to kAbsSubtree + 15 samples (e.g. 8 007 of an utterance of 15 999).  The
+// staging buffer is sized for that (round 2: it was sized for kAbsSubtree, and the samples beyond it raced with the slot
+// sums of faster threads - a wrong gain for utterance lengths just below 2^D * kAbsSubtree, found by scripts/soak.py).
+constexpr int kAbsSubtreeMax = kAbsSubtree + 16;
+constexpr int kAbs3Smem = kAbsSubtreeMax + 4 * (kAbsSubtreeMax / 128 + 1);
 __device__ __forceinline__ int abs3_pos(int i) { return i + ((i >> 7) << 2); }
 
 // Persistent CTAs.  Sub-tree records (source offset, length, heap slot) come
@@ -86,7 +91,7 @@ __global__ void __launch_bounds__(kAbs3Threads, 4) k_abs_pairwise4(const float* 
     __shared__ __align__(16) float hv[128];
     const int tid = threadIdx.x;
     const int G = gridDim.x;
-    constexpr int kIt = (kAbsSubtree / 4 + kAbs3Threads - 1) / kAbs3Threads;
+    constexpr int kIt = (kAbsSubtreeMax / 4 + kAbs3Threads - 1) / kAbs3Threads;
     AbsRec dummy; dummy.src_off = 0; dummy.heap_pos = 0; dummy.n = 0; dummy.pad = 0;
     int k = blockIdx.x;
     AbsRec cur = k < total ? recs[k] : dummy;

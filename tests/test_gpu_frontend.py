@@ -132,6 +132,9 @@ def test_gain_matches_numpy_bitwise(al):
     import torch
     rng = np.random.default_rng(3)
     lens = [1, 5, 8, 9, 127, 128, 129, 255, 1000, 4097, 7999, 8000, 8001, 16001, 48000, 64000, 100003, 1 << 20]
+    # lengths whose largest sub-tree exceeds 8 000 samples (NumPy's split rounds the left half down to a multiple of 8):
+    # 8 001 .. 8 015 samples in one staged sub-tree
+    lens += [15993, 15998, 15999, 31977, 31999, 63998, 63999, 127999, 255985, 8000 * 64 - 1]
     wavs = [(0.1 * rng.standard_normal(n)).astype(np.float32) for n in lens]
     plan = al.DspPlan.get(n_fft=400, win_length=400, hop_length=80)
     lay = al.FrontendLayout(lens, 80)
@@ -141,6 +144,16 @@ def test_gain_matches_numpy_bitwise(al):
     got = al.mean_abs_device(plan, dev, lay).cpu().numpy()
     want = np.array([np.abs(w).mean() for w in wavs], dtype=np.float32)
     np.testing.assert_array_equal(got, want)
+
+
+def test_lengths_just_below_a_subtree_multiple(al):
+    """Regression (scripts/soak.py): utterances of 2^D * 8000 - 1 .. - 7 samples stage a sub-tree of up to 8 015 samples in the
+    |y| kernel; the gain, and with it every feature above the amin clamp, must still match."""
+    rng = np.random.default_rng(21)
+    wavs = [(0.05 * rng.standard_normal(n)).astype(np.float32) for n in (15999, 31999, 15993)] + [synth.utterance(11, 4.0)[:63999]]
+    for y, g in zip(wavs, al.calc_MFCC_input_batch(wavs, **HP)):
+        for a, b, name in zip(g, oracle.calc_MFCC_input(y, **HP), ("mfcc", "mel", "pdb")):
+            assert_close(a, b, what=f"{name} (n = {len(y)})")
 
 
 def test_invalid_inputs_raise(al):

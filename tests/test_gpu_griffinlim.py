@@ -297,3 +297,19 @@ def test_zero_iterations_follow_the_reference(al):
     assert al.griffin_lim_alg(amp, 400, 80, num_iters=0, verbose=False) is None        # audio_lib.py:252 `wav = None`
     with pytest.raises(ValueError):
         al.from_power_to_wav(P, n_iter=0, verbose=False, **GL)
+
+
+def test_non_finite_result_raises_like_the_reference(al):
+    """An all-zero map with realse != 1 is 0 / 0 at audio_lib.py:296: the reference's librosa.stft then rejects the NaN
+    waveform from the second iteration on (found by scripts/soak.py); with one iteration no stft runs and NaN comes back."""
+    P = np.zeros((40, 201), dtype=np.float32)
+    kw = dict(GL); kw.update(verbose=False, realse=1.2, phase0=_phase0(5, (201, 40)))
+    with pytest.raises(ValueError):
+        al.from_power_to_wav(P, n_iter=3, **kw)
+    with pytest.raises(ValueError), np.errstate(all="ignore"):
+        oracle.from_power_to_wav(P, n_iter=3, **kw)
+    with np.errstate(all="ignore"):
+        assert np.isnan(oracle.from_power_to_wav(P, n_iter=1, **kw)).all()
+    assert np.isnan(al.from_power_to_wav(P, n_iter=1, **kw)).all()
+    kw["realse"] = 1.0                                            # no power law: amplitude 1e-4 everywhere, finite
+    assert np.isfinite(al.from_power_to_wav(P, n_iter=3, **kw)).all()
