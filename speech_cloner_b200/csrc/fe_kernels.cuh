@@ -562,10 +562,10 @@ k_fe_pass_b(Ragged rg, FeTables tb, FeParams prm, const UttStat* __restrict__ st
             }
             __syncwarp();
             if (lane == 0) {
-                float a = 0.f;
+                double a = 0.0;                                  // float64 sum like the DCT tasks below, rounded once
                 if (prm.norm_first)
-                    for (int n = 0; n < L.half; ++n) a = fmaf(__ldg(tb.dct_e + n * L.ne_pad), scratch[n], a);
-                c00_s[0] = a;
+                    for (int n = 0; n < L.half; ++n) a = fma((double)__ldg(tb.dct_e + n * L.ne_pad), (double)scratch[n], a);
+                c00_s[0] = (float)a;
             }
         }
     }
@@ -584,14 +584,20 @@ k_fe_pass_b(Ragged rg, FeTables tb, FeParams prm, const UttStat* __restrict__ st
             const float4* __restrict__ e4 = reinterpret_cast<const float4*>(dct_e + 4 * g);
             const float4* __restrict__ o4 = reinterpret_cast<const float4*>(dct_o + 4 * g);
             const int ld4 = L.ne_pad >> 2;
-            float ae0 = 0.f, ae1 = 0.f, ae2 = 0.f, ae3 = 0.f, ao0 = 0.f, ao1 = 0.f, ao2 = 0.f, ao3 = 0.f;
+            // float64 accumulators in the generic-size kernels: with many mel bands at the -100 dB clamp (128 bands on a short
+            // FFT) the float32 partial sums reach ~1 600 and their rounding alone is 1e-3 dB, the whole tolerance
+            // (scripts/soak2.py); each sum is rounded to float32 once, so MFCC[0, 0] - MFCC[0, 0] stays exactly 0
+            double de0 = 0.0, de1 = 0.0, de2 = 0.0, de3 = 0.0, do0 = 0.0, do1 = 0.0, do2 = 0.0, do3 = 0.0;
 #pragma unroll 4
             for (int n = 0; n < L.half; ++n) {
                 const float2 v = x[n];
                 const float4 e = e4[n * ld4], o = o4[n * ld4];
-                ae0 = fmaf(e.x, v.x, ae0); ae1 = fmaf(e.y, v.x, ae1); ae2 = fmaf(e.z, v.x, ae2); ae3 = fmaf(e.w, v.x, ae3);
-                ao0 = fmaf(o.x, v.y, ao0); ao1 = fmaf(o.y, v.y, ao1); ao2 = fmaf(o.z, v.y, ao2); ao3 = fmaf(o.w, v.y, ao3);
+                const double vx = (double)v.x, vy = (double)v.y;
+                de0 = fma((double)e.x, vx, de0); de1 = fma((double)e.y, vx, de1); de2 = fma((double)e.z, vx, de2); de3 = fma((double)e.w, vx, de3);
+                do0 = fma((double)o.x, vy, do0); do1 = fma((double)o.y, vy, do1); do2 = fma((double)o.z, vy, do2); do3 = fma((double)o.w, vy, do3);
             }
+            float ae0 = (float)de0, ae1 = (float)de1, ae2 = (float)de2, ae3 = (float)de3;
+            const float ao0 = (float)do0, ao1 = (float)do1, ao2 = (float)do2, ao3 = (float)do3;
             if (g == 0) ae0 -= c00;
             float* __restrict__ c = cc_s + r * L.cc_ld + 8 * g;
             c[0] = sc * ae0; c[1] = sc * ao0; c[2] = sc * ae1; c[3] = sc * ao1;
@@ -628,7 +634,7 @@ __global__ void __launch_bounds__(128) k_fe_c00(Ragged rg, FeTables tb, FeParams
     const int u = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (u >= rg.n_utts) return;
     const int lane = threadIdx.x & 31;
-    float a = 0.f;
+    double a = 0.0;                                              // same float64 chain as coefficient 0 of k_fe_pass_b2
     if (prm.norm_first) {
         const int n_mels = tb.n_mels;
         const FbLayout L = fb_layout(n_mels, tb.n_mfcc);
@@ -648,11 +654,11 @@ __global__ void __launch_bounds__(128) k_fe_c00(Ragged rg, FeTables tb, FeParams
             }
         }
         for (int n = 0; n < min(L.half, 32); ++n)
-            a = fmaf(__shfl_sync(0xffffffffu, ev[0], n), __shfl_sync(0xffffffffu, sv[0], n), a);
+            a = fma((double)__shfl_sync(0xffffffffu, ev[0], n), (double)__shfl_sync(0xffffffffu, sv[0], n), a);
         for (int n = 32; n < L.half; ++n)
-            a = fmaf(__shfl_sync(0xffffffffu, ev[1], n - 32), __shfl_sync(0xffffffffu, sv[1], n - 32), a);
+            a = fma((double)__shfl_sync(0xffffffffu, ev[1], n - 32), (double)__shfl_sync(0xffffffffu, sv[1], n - 32), a);
     }
-    if (lane == 0) stat[u].pad[0] = a;
+    if (lane == 0) stat[u].pad[0] = (float)a;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -806,14 +812,20 @@ k_fe_pass_b2(Ragged rg, FeTables tb, FeParams prm, const UttStat* __restrict__ s
             const float2* __restrict__ x = sd_s + r * L.sd_ld;
             const float4* __restrict__ e4 = reinterpret_cast<const float4*>(dct_e) + g;
             const float4* __restrict__ o4 = reinterpret_cast<const float4*>(dct_o) + g;
-            float ae0 = 0.f, ae1 = 0.f, ae2 = 0.f, ae3 = 0.f, ao0 = 0.f, ao1 = 0.f, ao2 = 0.f, ao3 = 0.f;
+            // float64 accumulators in the generic-size kernels: with many mel bands at the -100 dB clamp (128 bands on a short
+            // FFT) the float32 partial sums reach ~1 600 and their rounding alone is 1e-3 dB, the whole tolerance
+            // (scripts/soak2.py); each sum is rounded to float32 once, so MFCC[0, 0] - MFCC[0, 0] stays exactly 0
+            double de0 = 0.0, de1 = 0.0, de2 = 0.0, de3 = 0.0, do0 = 0.0, do1 = 0.0, do2 = 0.0, do3 = 0.0;
 #pragma unroll 8
             for (int n = 0; n < L.half; ++n) {
                 const float2 v = x[n];
                 const float4 e = e4[n * ld4], o = o4[n * ld4];
-                ae0 = fmaf(e.x, v.x, ae0); ae1 = fmaf(e.y, v.x, ae1); ae2 = fmaf(e.z, v.x, ae2); ae3 = fmaf(e.w, v.x, ae3);
-                ao0 = fmaf(o.x, v.y, ao0); ao1 = fmaf(o.y, v.y, ao1); ao2 = fmaf(o.z, v.y, ao2); ao3 = fmaf(o.w, v.y, ao3);
+                const double vx = (double)v.x, vy = (double)v.y;
+                de0 = fma((double)e.x, vx, de0); de1 = fma((double)e.y, vx, de1); de2 = fma((double)e.z, vx, de2); de3 = fma((double)e.w, vx, de3);
+                do0 = fma((double)o.x, vy, do0); do1 = fma((double)o.y, vy, do1); do2 = fma((double)o.z, vy, do2); do3 = fma((double)o.w, vy, do3);
             }
+            float ae0 = (float)de0, ae1 = (float)de1, ae2 = (float)de2, ae3 = (float)de3;
+            const float ao0 = (float)do0, ao1 = (float)do1, ao2 = (float)do2, ao3 = (float)do3;
             if (g == 0) ae0 -= c00;
             float4* __restrict__ c = reinterpret_cast<float4*>(cc_s + r * L.cc_ld + 8 * g);
             c[0] = make_float4(sc * ae0, sc * ao0, sc * ae1, sc * ao1);
@@ -871,7 +883,7 @@ struct B3Tile {
 // the separate k_fe_c00 launch of round 1).
 __device__ __forceinline__ void b3_dct_group(const float4* __restrict__ e4, const float4* __restrict__ o4,
                                              const float2* __restrict__ x, bool first_group, bool norm_first, bool store,
-                                             float sc, float* __restrict__ out) {
+                                             float sc, float c0_shift, float* __restrict__ out) {
     float ae0 = 0.f, ae1 = 0.f, ae2 = 0.f, ae3 = 0.f, ao0 = 0.f, ao1 = 0.f, ao2 = 0.f, ao3 = 0.f;
 #pragma unroll 8
     for (int n = 0; n < kB3Half; ++n) {
@@ -882,7 +894,8 @@ __device__ __forceinline__ void b3_dct_group(const float4* __restrict__ e4, cons
     }
     if (first_group) {                                               // warp-uniform: one warp per coefficient group
         const float c00 = __shfl_sync(0xffffffffu, ae0, kB3Rows);
-        if (norm_first) ae0 -= c00;
+        // the rows are centred (see the fold): the centre cancels in MFCC[t, 0] - MFCC[0, 0], otherwise it is added back
+        ae0 = norm_first ? ae0 - c00 : ae0 + c0_shift;
     }
     if (store) {
         float4* __restrict__ c = reinterpret_cast<float4*>(out);
@@ -918,6 +931,14 @@ k_fe_pass_b3(const B3Tile* __restrict__ tiles, int total_tiles, FeTables tb, FeP
     constexpr int kMelIt = (kB3Rows * (kB3Mels / 8) + kB3Threads - 1) / kB3Threads;     // 2
     constexpr int kQRow = kB3Mels / 8, kRow4 = kB3Mels / 4;
     for (int e = tid; e < kB3Half * (kB3Mfcc / 2); e += kB3Threads) { dct_e[e] = tb.dct_e[e]; dct_o[e] = tb.dct_o[e]; }
+    // sum of the folded coefficient-0 weights: what a constant added to every mel band contributes to MFCC[:, 0]
+    __shared__ float k0_s;
+    if (tid == 0) {
+        double k0 = 0.0;
+        for (int n = 0; n < kB3Half; ++n) k0 += (double)tb.dct_e[n * (kB3Mfcc / 2)];
+        k0_s = (float)(2.0 * k0);
+    }
+    __syncthreads();
 
     float4 pv[kPdbIt], a[kMelIt], b[kMelIt];
     float c0a = 0.f, c0b = 0.f;            // frame 0 of the utterance, raw mel dB bins tid and 79 - tid (threads 0..39)
@@ -960,16 +981,23 @@ k_fe_pass_b3(const B3Tile* __restrict__ tiles, int total_tiles, FeTables tb, FeP
         const int nfr = min(kB3Frames, T - t0);
         const int64_t row0 = tl.frame_off + t0;
         const int64_t frame_off = tl.frame_off;
+        float c0_shift;
         // ---- mel dB rows t0-1 .. t0+nfr (halo for the delta): clip (:172), normalised rows out (:235, :240), fold
         {
             const float m_hi = 2.0f * db10(fmaxf(__uint_as_float(st.m_max), 1e-5f));
             const float m_floor = m_hi - 80.0f;
+            // The DCT sums float32 products of values that all lie in [m_floor, m_hi]: centred on the middle of that range
+            // they are at most 40 in magnitude instead of up to 100, which cuts the rounding of the 40-term chains (7e-6 of
+            // the 1e-5 tolerance, measured against float64 sums) by the same factor.  A constant moves only coefficient 0
+            // (the odd ones see differences, the even basis rows sum to zero), see b3_dct_group.
+            const float ctr = m_hi - 40.0f;
+            c0_shift = ctr * k0_s;
             const float m_lo = fmaxf(2.0f * db10(fmaxf(__uint_as_float(st.m_min), 1e-5f)), m_floor);
             const float sub = prm.shift_m ? m_lo : 0.0f;
             const float mul = prm.shift_m ? prm.m_db_norm_factor : 1.0f;
             float4* __restrict__ dst = reinterpret_cast<float4*>(mel_out + frame_off * kB3Mels);
             // folded, clipped frame 0 of the utterance (for MFCC[0, 0]): s[n] = x[n] + x[79-n], same operations as below
-            if (tid < kB3Half) sd_s[kB3Rows * kB3SdLd + tid] = make_float2(fmaxf(c0a, m_floor) + fmaxf(c0b, m_floor), 0.f);
+            if (tid < kB3Half) sd_s[kB3Rows * kB3SdLd + tid] = make_float2((fmaxf(c0a, m_floor) - ctr) + (fmaxf(c0b, m_floor) - ctr), 0.f);
 #pragma unroll
             for (int it = 0; it < kMelIt; ++it) {
                 const int task = tid + it * kB3Threads;
@@ -985,6 +1013,8 @@ k_fe_pass_b3(const B3Tile* __restrict__ tiles, int total_tiles, FeTables tb, FeP
                         B3_ST(dst + (int64_t)t * kRow4 + m4, fb2_norm(xa, sub, mul, cl));
                         B3_ST(dst + (int64_t)t * kRow4 + (kRow4 - 1 - m4), fb2_norm(xb, sub, mul, cl));
                     }
+                    xa.x -= ctr; xa.y -= ctr; xa.z -= ctr; xa.w -= ctr;
+                    xb.x -= ctr; xb.y -= ctr; xb.z -= ctr; xb.w -= ctr;
                     sd[0] = make_float2(xa.x + xb.w, xa.x - xb.w);
                     sd[1] = make_float2(xa.y + xb.z, xa.y - xb.z);
                     sd[2] = make_float2(xa.z + xb.y, xa.z - xb.y);
@@ -1024,7 +1054,7 @@ k_fe_pass_b3(const B3Tile* __restrict__ tiles, int total_tiles, FeTables tb, FeP
             const int lane = tid & 31, g = tid >> 5;
             const int row = lane <= kB3Rows ? lane : 0;                 // lane kB3Rows: frame 0 of the utterance; lane 31 idles on row 0
             b3_dct_group(reinterpret_cast<const float4*>(dct_e) + g, reinterpret_cast<const float4*>(dct_o) + g,
-                         sd_s + row * kB3SdLd, g == 0, prm.norm_first != 0, lane < kB3Rows, prm.mfcc_norm_factor,
+                         sd_s + row * kB3SdLd, g == 0, prm.norm_first != 0, lane < kB3Rows, prm.mfcc_norm_factor, c0_shift,
                          cc_s + row * kB3CcLd + 8 * g);
         }
         __syncthreads();

@@ -221,7 +221,8 @@ def test_tightly_packed_unaligned_offsets(al):
     ref = al.calc_MFCC_input_batch(wavs, **HP)
     for u, (o, t) in enumerate(zip(fo, lay.frames)):
         for got, want, name in zip((mfcc[o:o + t], mel[o:o + t], pdb[o:o + t]), ref[u], ("MFCC", "M_dB", "P_dB")):
-            assert_close(got, want, rtol=1e-6, atol=2e-7, what=f"utt {u}/{name}")
+            # same arithmetic up to the DCT sums: float64 in the scalar pass B, centred float32 chains in the hp pass B
+            assert_close(got, want, rtol=1e-6, atol=5e-6 if name == "MFCC" else 2e-7, what=f"utt {u}/{name}")
 
 
 @pytest.mark.parametrize("n_chunks,n_streams,ramp", [(8, 3, True), (3, 2, False), (64, 4, True), (1, 1, True)])
