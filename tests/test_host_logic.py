@@ -101,3 +101,47 @@ def test_signatures_match_the_reference_source():
         assert got[:len(want[name])] == want[name], name
         extra = got[len(want[name]):]
         assert all(e[0] in ("phase0",) for e in extra), f"{name}: only the documented phase0 keyword may be added, got {extra}"
+
+
+def test_pairwise_subtree_bound_of_the_abs_kernel():
+    """The |y| kernel stages one sub-tree of NumPy's pairwise summation per CTA (csrc/fe_kernels.cuh).  NumPy splits a node
+    at n/2 rounded DOWN to a multiple of 8, so the sub-trees at depth abs_depth(n) hold up to kAbsSubtree + 15 samples,
+    not kAbsSubtree - the bound the staging buffer (kAbsSubtreeMax = kAbsSubtree + 16) and the seven slot levels rely on.
+    The constants are read from the source so that the test follows the kernel."""
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "speech_cloner_b200", "csrc",
+                            "fe_kernels.cuh")).read()
+    K = int(re.search(r"#define SC_ABS_SUBTREE (\d+)", src).group(1))
+    slack = int(re.search(r"kAbsSubtreeMax = kAbsSubtree \+ (\d+)", src).group(1))
+
+    def depth(n):
+        d = 0
+        while (n >> d) > K:
+            d += 1
+        return d
+
+    def split(sizes):
+        out = []
+        for x in sizes:
+            n2 = x // 2
+            n2 -= n2 % 8
+            out += [n2, x - n2]
+        return out
+
+    def subtrees(n):
+        s = [n]
+        for _ in range(depth(n)):
+            s = split(s)
+        return s
+
+    rng = np.random.default_rng(0)
+    lengths = {K * (1 << D) + k for D in range(9) for k in range(-40, 3)} | {int(x) for x in rng.integers(1, 1 << 21, size=4000)}
+    worst = max(max(subtrees(n)) for n in lengths if n > 0)
+    assert K < worst <= K + slack - 1                    # the bound is real (8 015 at K = 8 000) and inside the buffer
+    # seven more levels bring every sub-tree of up to K + slack samples down to leaves NumPy sums without splitting
+    for s in list(range(K - 40, K + slack + 1)) + [int(x) for x in rng.integers(129, K, size=300)]:
+        leaves = [s]
+        for _ in range(7):
+            leaves = [y for x in leaves for y in (split([x]) if x > 128 else [x])]
+        assert max(leaves) <= 128
