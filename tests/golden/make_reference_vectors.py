@@ -38,6 +38,8 @@ FE_CASES = [  # (name, first seed to try, seconds, ds_norm, keyword overrides)
     ("signature_defaults", 5200, 0.3, (0.0, 1.0), None),          # calc_MFCC_input(y): hop 40, 128 mels, no delta
     ("hamming_nodelta_noclip", 5300, 0.4, (0.0, 1.0), {"window": "hamming", "calc_mfcc_derivate": False,
                                                        "clip_output": False}),
+    # 15 999 samples: NumPy's pairwise sum of |y| has a sub-tree of 8 007 samples here (finding 5)
+    ("len_15999", 5400, 15999 / 16000.0, (0.0, 1.0), {}),
 ]
 GL_CASES = [  # (name, seed, frames, iterations, realse)
     ("gl_10", 6000, 50, 10, 1.0),
