@@ -104,3 +104,24 @@ def test_config3_batch_64_against_the_oracle_at_200_iterations(al):
         want = oracle.from_power_to_wav(Ps[i], n_fft=None, verbose=False, phase0=phs[i], **kw)
         assert snr_db(out[i], want) >= 40.0, i
         np.testing.assert_allclose(np.abs(out[i]).mean(), 0.045, rtol=1e-9)
+
+
+def test_config5_shaped_sweep_is_consistent(al):
+    """configs[4] in the shape bench.py times it (16 distinct TIMIT-shaped 3 s + 16 ARCTIC-shaped 4 s utterances tiled), at a
+    tenth of the 10 h: every replica of an utterance must give the same bits wherever it sits in the ragged batch (tile
+    tables, packed offsets beyond 2^31 bytes are 64-bit), and the distinct ones must match the oracle."""
+    import torch
+    timit = synth.batch(5, 16, 3.0, ds_norm=(0.0, 10.0))
+    arctic = synth.batch(6, 16, 4.0)
+    wavs = [timit[i % 16] for i in range(600)] + [arctic[i % 16] for i in range(450)]
+    dev = [torch.from_numpy(w).cuda() for w in timit + arctic]
+    feats = al.calc_MFCC_input_batch([dev[i % 16] for i in range(600)] + [dev[16 + i % 16] for i in range(450)], **HP)
+    assert len(feats) == 1050
+    for i, f in enumerate(feats):
+        first = feats[i % 16] if i < 600 else feats[600 + (i - 600) % 16]
+        for a, b in zip(f, first):
+            assert a.shape == b.shape and torch.equal(a, b), f"replica {i} differs from its first copy"
+    for i in (0, 7, 600, 611, 1049):
+        want = oracle.calc_MFCC_input(wavs[i], **HP)
+        for a, b in zip(feats[i], want):
+            assert_close(a.cpu().numpy(), b, what=f"utt {i}")
